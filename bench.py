@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- ln-posterior evaluations per second of the full NC+Fe+HG+BC model.
+
+    python bench.py --gpus N --steps K --warmup W            (our CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   (the CPU restatement of
+                                                               the reference, all host cores)
+
+A "step" is one batched ln-posterior call over the rank's walker ensemble
+(BASELINE.json config 5: 8192 walkers x 8192 pixels, D = 20, FP64), parameters
+already resident in HBM, followed -- when N > 1 -- by the all-gather of the
+per-walker ln-probabilities (the only exchange of the stretch move).  One JSON
+line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ln-posterior evals/sec (walkers x steps), full NC+Fe+HG+BC model, 8k px"
+UNIT = "evals/s"
+N_PIX = 8192
+N_WALKERS = 8192
+COMPONENTS = ("PL", "FE", "HOST", "BC")
+
+
+# ---------------------------------------------------------------------------
+# algorithmic work per evaluation
+# ---------------------------------------------------------------------------
+def algorithmic_flops(wl, fe_ranges, n_host=7, n_host_pts=4771):
+    """F = 3P [NC] + sum_t(2 N_t Mbar_t + 6 P_t) [Fe] + 7 (2 N_h Mbar_h + 6 P) [host]
+         + 22 P [BC] + 6*397*(P_red+1) [BpC] + 5 P [chi^2]."""
+    P = len(wl)
+    n_t = (4181, 584, 4000)
+    mbar_t = (91.3, 100.0, 121.3)
+    p_t = [int(((wl >= lo) & (wl <= hi)).sum()) for lo, hi in fe_ranges]
+    p_red = int((wl > 3646.0).sum())
+    f_nc = 3 * P
+    f_fe = sum(2 * n * m + 6 * p for n, m, p in zip(n_t, mbar_t, p_t))
+    f_host = n_host * (2 * n_host_pts * 16.5 + 6 * P)
+    f_bc = 22 * P
+    f_bpc = 6 * 397 * (p_red + 1)
+    f_chi = 5 * P
+    return float(f_nc + f_fe + f_host + f_bc + f_bpc + f_chi)
+
+
+FE_RANGES = ((1074.987, 3089.96), (3090.0, 3534.0), (3535.0, 7535.0))
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi sampled every 100 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                c, cm, pw = float(parts[0]), float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(c)
+                smax.append(cm)
+                power.append(pw)
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)),
+                "power_w_max": float(np.max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU baseline: the numpy restatement of the reference, one process per core
+# ---------------------------------------------------------------------------
+_ORACLE = None
+
+
+def _oracle_init(wl, flux, err):
+    global _ORACLE
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle.spamm_numpy import OracleModel
+    _ORACLE = OracleModel(wl, flux, err, comps=list(COMPONENTS))
+    _ORACLE.bounds()
+
+
+def _oracle_eval(p):
+    return _ORACLE.ln_posterior(p)
+
+
+def oracle_workload(n_walkers, seed=42):
+    """Same workload built without touching the GPU path (reference arm)."""
+    from oracle.spamm_numpy import OracleModel
+    wl = 1000.0 + np.arange(N_PIX) * (9000.0 / N_PIX)
+    truth = {"PL": [5e-15, 2.3], "FE": [1.07988504e-14, 6.91877436e-15, 5e-15, 5450.],
+             "HOST": [5e-17, 5.5e-17, 5e-16, 1e-16, 2e-16, 3e-16, 4e-16, 515.],
+             "BC": [3e-14, 50250., 1.0, 0.0, 5050., 5.5]}
+    o0 = OracleModel(wl, wl, wl, comps=list(COMPONENTS))
+    fl = [o0.component_flux(c, truth[c]) for c in COMPONENTS]
+    flux = np.sum(fl, axis=0)
+    err = np.sqrt(np.sum([(0.05 * f) ** 2 for f in fl], axis=0))
+    o = OracleModel(wl, flux, err, comps=list(COMPONENTS))
+    np.random.seed(seed)
+    params = np.array([o.initial_values() for _ in range(n_walkers)])
+    return wl, flux, err, params
+
+
+def cpu_pool_throughput(wl, flux, err, params, cores, repeats=1):
+    """evals/s of multiprocessing.Pool(cores).map(ln_posterior, walkers) -- what
+    emcee's threads=n does with the reference (spamm/Model.py:283-286)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_oracle_init, initargs=(wl, flux, err)) as pool:
+        pool.map(_oracle_eval, list(params[:cores]))       # warm the workers
+        best = 0.0
+        vals = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            vals = pool.map(_oracle_eval, list(params), chunksize=max(1, len(params) // (4 * cores)))
+            dt = time.perf_counter() - t0
+            best = max(best, len(params) / dt)
+    return best, np.array(vals)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = max(8 * cores, 64)
+    n = per_step * (args.steps + args.warmup)
+    wl, flux, err, params = oracle_workload(min(n, 4096))
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores, initializer=_oracle_init, initargs=(wl, flux, err)) as pool:
+        for s in range(args.warmup + args.steps):
+            chunk = params[(s * per_step) % len(params):][:per_step]
+            if len(chunk) < per_step:
+                chunk = params[:per_step]
+            t0 = time.perf_counter()
+            pool.map(_oracle_eval, list(chunk), chunksize=max(1, per_step // (4 * cores)))
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    total = float(np.sum(times))
+    value = per_step * args.steps / total
+    sample = "%d walkers per step x %d steps of the config-5 ensemble, numpy port of the reference, " \
+             "multiprocessing.Pool(%d)" % (per_step, args.steps, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "config5: full NC+Fe+HG+BC, 8192 px, D=20, walkers from priors (seed 42)",
+                   "walkers_per_step": per_step, "n_pix": N_PIX},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from spamm_b200 import _lib
+    from spamm_b200.distributed import init_from_env
+    from spamm_b200.synth import full_model_workload
+
+    rank, world, local_rank = init_from_env("nccl")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+
+    n_local = args.walkers
+    if args.scaling == "strong":
+        n_local = (args.walkers + world - 1) // world
+    model, params_all = full_model_workload(N_PIX, args.walkers if args.scaling == "strong" else args.walkers,
+                                            seed=42 + (rank if args.scaling == "weak" else 0))
+    if args.scaling == "strong":
+        params_host = np.ascontiguousarray(params_all[rank * n_local:(rank + 1) * n_local])
+        n_local = len(params_host)
+    else:
+        params_host = params_all
+    plan = model.plan
+    params = torch.from_numpy(params_host).to(dev)
+    lnp = torch.empty(n_local, dtype=torch.float64, device=dev)
+    gathered = torch.empty(n_local * world, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        plan.lnposterior(params, out=lnp)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lnp)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP64 peak for the roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
+    import ctypes
+    peak = ctypes.c_double(0.0)
+    _lib.check(lib.spamm_fp64_peak_probe(20000, 5, ctypes.byref(peak)))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    launches0 = plan.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.time()
+    for e0, e1 in evs:
+        flush.zero_()                    # L2 flush between timed iterations (untimed)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = plan.launch_count - launches0
+    ms = np.array([e0.elapsed_time(e1) for e0, e1 in evs])
+    total_ms = float(ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # end to end through the public API with host buffers (H2D + kernel + D2H every step)
+    e2e_steps = max(3, min(args.steps, 10))
+    model.lnposterior_batch(params_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = model.lnposterior_batch(params_host)
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = n_local * world * e2e_steps / t_e2e
+    assert np.array_equal(res, lnp.cpu().numpy()), "host-buffer and device-buffer paths disagree"
+
+    value = n_local * world * args.steps / (total_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        wl = np.asarray(model.data_spectrum.spectral_axis)
+        flops = algorithmic_flops(wl, FE_RANGES)
+        achieved = flops * (n_local * args.steps / (total_ms * 1e-3)) / 1e12    # this GPU's share
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
+                    "frac": achieved / float(peak.value) if peak.value else None, "traffic": None,
+                    "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); "
+                                   "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
+                    "algorithmic_flops_per_eval": flops, "kernel": "k_walkers<0>"}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu = max(4 * cores, 64)
+            v, vals = cpu_pool_throughput(wl, np.asarray(model.data_spectrum.flux),
+                                          np.asarray(model.data_spectrum.flux_error),
+                                          params_host[:n_cpu], cores)
+            gpu_vals = res[:n_cpu]
+            rel = float(np.max(np.abs(vals - gpu_vals) / np.abs(vals)))
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first %d walkers of the same ensemble, numpy port of the reference, "
+                             "multiprocessing.Pool(%d).map" % (n_cpu, cores),
+                   "max_rel_diff_vs_gpu": rel}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config5: full NC+Fe+HG+BC, 8192 px, D=20, walkers from priors (seed 42)",
+                       "walkers_per_gpu": n_local, "walkers_total": n_local * world, "n_pix": N_PIX,
+                       "l2": "256 MiB flush between timed steps", "parallelism": "walkers sharded x%d, "
+                       "all-gather of ln-probs per step" % world,
+                       "template_mode": "bank" if plan.template_mode == _lib.TEMPLATES_BANK else "direct"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_host.nbytes),
+                    "d2h_bytes_per_step": int(n_local * 8), "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "ms_per_step_minmax": [float(ms.min()), float(ms.max())],
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers", type=int, default=N_WALKERS, help="walkers per GPU (weak) / total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,153 @@
+"""Model + ln-posterior with the reference's surface (spamm/Model.py): the
+`components` list fixes the parameter layout, `data_spectrum = ...` initialises
+the components, and `ln_posterior(new_params, model)` is what a sampler calls.
+
+Underneath, every flux / likelihood / ln-posterior evaluation is one batched
+CUDA call through the C ABI (include/spamm_b200.h).  New, batched entry points:
+`Model.lnposterior_batch(params[W, D])`, `Model.model_flux_batch`, and
+`GpuPool` (spamm_b200/sampler.py) for an unmodified emcee."""
+import sys
+
+import numpy as np
+
+from .Spectrum import Spectrum
+from . import _lib
+
+iteration_count = 0
+
+
+class MCMCDidNotConverge(Exception):
+    pass
+
+
+def ln_posterior(new_params, *args):
+    """ln(prior) + ln(likelihood) of one parameter vector; -inf outside the
+    priors (Model.py:42-79).  args[0] is the Model."""
+    global iteration_count
+    iteration_count = iteration_count + 1
+    model = args[0]
+    return float(model.lnposterior_batch(np.asarray(new_params, dtype=np.float64)[None, :])[0])
+
+
+class Model(object):
+    """
+    Attributes:
+        components (list): component plugins; list order = parameter order.
+        data_spectrum (Spectrum): setting it initialises every component.
+        model_spectrum (Spectrum): wavelength grid + last model flux.
+        sampler: the ensemble sampler after run_mcmc.
+    """
+
+    def __init__(self, wavelength_start=1000, wavelength_end=10000, wavelength_delta=0.05, mpi=False):
+        self._mask = None
+        self._data_spectrum = None
+        self.z = None
+        self.components = []
+        self.mpi = mpi
+        self.sampler = None
+        # the data spectrum defines the model grid (Model.py:189); no 180k-point
+        # placeholder grid is allocated up front
+        self._init_grid = (wavelength_start, wavelength_end, wavelength_delta)
+        self.model_spectrum = Spectrum(spectral_axis=np.zeros(0), flux=np.zeros(0), flux_error=np.zeros(0))
+        self.downsample_data_if_needed = False
+        self.upsample_components_if_needed = False
+        self.print_parameters = False
+        self.max_walkers = 8192
+        self.template_mode = _lib.TEMPLATES_AUTO
+        self._plan = None
+
+    # -- data ----------------------------------------------------------------------
+    @property
+    def data_spectrum(self):
+        """All components of the model must be set before setting the data."""
+        return self._data_spectrum
+
+    @data_spectrum.setter
+    def data_spectrum(self, new_data_spectrum):
+        self._data_spectrum = new_data_spectrum
+        if len(self.components) == 0:
+            raise Exception("Components must be added before defining the data spectrum.")
+        self.model_spectrum.spectral_axis = np.array(new_data_spectrum.spectral_axis)
+        self.model_spectrum.flux = np.zeros(len(self.model_spectrum.spectral_axis))
+        for component in self.components:
+            component.initialize(data_spectrum=new_data_spectrum)
+        # template components report no grid spacing (App. B Q9), so the model grid
+        # is always the data grid and no resampling branch exists here
+        self._plan = None
+
+    # -- plan ------------------------------------------------------------------------
+    @property
+    def plan(self):
+        """Device plan, built on first use (after the prior sentinels can be resolved)."""
+        if self._plan is None:
+            if self._data_spectrum is None:
+                raise Exception("Set data_spectrum before evaluating the model.")
+            from .plan import ModelPlan
+            self._plan = ModelPlan(self.components, self._data_spectrum, max_walkers=self.max_walkers,
+                                   template_mode=self.template_mode)
+        return self._plan
+
+    def invalidate_plan(self):
+        self._plan = None
+
+    # -- sampler -----------------------------------------------------------------------
+    def initial_walkers(self, n_walkers):
+        """Walker matrix drawn from the priors, component by component (Model.py:254-259)."""
+        walkers_matrix = []
+        for walker in range(n_walkers):
+            walker_params = []
+            for component in self.components:
+                walker_params = walker_params + component.initial_values(self.data_spectrum)
+            walkers_matrix.append(walker_params)
+        return walkers_matrix
+
+    def run_mcmc(self, n_walkers=100, n_iterations=100, seed=None):
+        """Run the ensemble sampler (emcee 2.2.1 stretch move, on the device)."""
+        from .sampler import EnsembleSampler
+        walkers_matrix = self.initial_walkers(n_walkers)
+        global iteration_count
+        iteration_count = 0
+        self.sampler = EnsembleSampler(nwalkers=n_walkers, dim=len(walkers_matrix[0]),
+                                       lnpostfn=ln_posterior, args=[self], seed=seed)
+        self.sampler.run_mcmc(walkers_matrix, n_iterations)
+
+    # -- bookkeeping ------------------------------------------------------------------
+    @property
+    def total_parameter_count(self):
+        return sum(c.parameter_count for c in self.components)
+
+    def model_parameter_names(self):
+        labels = []
+        for c in self.components:
+            labels = labels + [x for x in c.model_parameter_names]
+        return labels
+
+    # -- evaluation ------------------------------------------------------------------------
+    def model_flux_batch(self, params):
+        """[W, D] -> [W, P] summed component fluxes (Model.model_flux, Model.py:328-366)."""
+        return self.plan.model_flux_host(params)
+
+    def model_flux(self, params):
+        if self.print_parameters:
+            print("params = {0}".format(params))
+        self.model_spectrum.flux = self.model_flux_batch(np.asarray(params, dtype=np.float64)[None, :])[0]
+        return self.model_spectrum.flux
+
+    def likelihood(self, model_spectrum_flux):
+        """ln L of a model flux on the data grid (Model.py:418-445)."""
+        import torch
+        m = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(model_spectrum_flux), dtype=np.float64)).cuda()
+        return float(self.plan.likelihood(m).cpu().numpy()[0])
+
+    def prior(self, params):
+        """Sum of the components' ln-priors (Model.py:449-470)."""
+        p = np.copy(params)
+        ln_p = 0
+        for component in self.components:
+            ln_p += sum(component.ln_priors(params=p[0:component.parameter_count]))
+            p = p[component.parameter_count:]
+        return ln_p
+
+    def lnposterior_batch(self, params):
+        """ln-posterior of a whole walker ensemble in one call: numpy [W, D] -> numpy [W]."""
+        return self.plan.lnposterior_host(params)

@@ -1,0 +1,54 @@
+"""In-tree build of libspamm_b200.so (nvcc, sm_100a).  Used by
+``__graft_entry__.build()`` and ``python -m spamm_b200._build``."""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+SRC = os.path.join(PKG, "csrc", "spamm_b200.cu")
+INC = os.path.join(ROOT, "include")
+OUT = os.path.join(PKG, "libspamm_b200.so")
+
+# -fmad=false: no implicit FMA contraction -- integer decisions (sigma_norm,
+# edge pixel, interp bins) must round exactly like the numpy reference.
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libspamm_b200.so")
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [SRC, os.path.join(INC, "spamm_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", INC, "-o", OUT, SRC]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)

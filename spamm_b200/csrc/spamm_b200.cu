@@ -1,0 +1,1417 @@
+// spamm_b200 -- hand-written sm_100a kernels for the SPAMM ln-posterior hot path
+// and the C ABI declared in include/spamm_b200.h.
+//
+// Compiled with -fmad=false: every multiply/add is rounded separately, exactly
+// as written (the reference is numpy on x86-64 without FMA contraction; the
+// integer decisions -- sigma_norm = ceil(..), argmin edge pixel, interp bins --
+// must come out bit-identical).  FMAs are used only where written explicitly
+// as fma() (hot inner loops where a 1-ulp difference is harmless).
+//
+// Reference call sites are cited as file:line relative to the reference root.
+//   Model.py            = spamm/Model.py
+//   NC / Fe / HG / BC   = spamm/components/{NuclearContinuumComponent,FeComponent,
+//                          HostGalaxyComponent,BalmerContinuumCombined}.py
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "spamm_b200.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            return set_error(SPAMM_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                  \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device-side plan
+// ---------------------------------------------------------------------------
+constexpr int kThreads = 256;          // threads per CTA of the fused kernel
+constexpr int kPix = 2;                // pixels per thread in the line loop
+constexpr int kMaxDim = 64;            // max parameters per walker
+constexpr int kMaxLines = 1024;
+constexpr int kConvTile = 256;
+
+enum StatusBits : int {
+    kStatSigmaRange = 1,   // sigma_norm outside the bank / < 1
+    kStatBcKernel = 2,     // log_conv kernel wider than one pixel (unsupported)
+    kStatBcStage = 4,      // BC edge pixel beyond the staged f0 range
+};
+
+struct TemplDev {
+    int n_templ;
+    int n_pts[SPAMM_MAX_TEMPLATES];
+    int off[SPAMM_MAX_TEMPLATES];        // offsets into logx/logf
+    double bin[SPAMM_MAX_TEMPLATES];     // x[2]-x[1]  (Fe:288)
+    double norm_wl[SPAMM_MAX_TEMPLATES];
+    int bank_row0[SPAMM_MAX_TEMPLATES];
+    int bank_sig_max[SPAMM_MAX_TEMPLATES];
+    double templ_width, sigma_denom, sqrt_2pi;
+    int ksize, clamp;
+    int param_off;                        // first parameter of this component
+    const double* logx;
+    const double* logf;
+    const double* bank_f;                 // [rows][P]
+    const double* bank_nf;                // [rows]
+};
+
+struct PlanDev {
+    int P, D;
+    const double *wl, *lnwl, *flux, *err;
+    double sum_ln;
+    const double *lo, *hi;                // may be null
+    // components: bit index -> kind ; parameter offsets
+    int n_comp;
+    int comp_kind[SPAMM_MAX_COMPONENTS];
+    int comp_off[SPAMM_MAX_COMPONENTS];
+    // NC
+    int nc_broken;
+    const double* nc_x;                   // wl / norm_wl
+    // templates
+    TemplDev fe, host;
+    // Balmer
+    int bc_on, bpc_on, line_type, line_min, n_lines, n_lines_pad;
+    const double *line_c0, *line_e;
+    double sh_ne[SPAMM_SH95_NE], sh_T[SPAMM_SH95_T];
+    const double* sh_z;
+    const double *bc_hnu, *bc_b1, *bc_lam2, *bc_t3, *bc_lnnew, *bc_expnew;
+    const int *bc_jA, *bc_kB;
+    int bc_nstage;
+    double bc_dlnew;
+    double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
+    int* status;
+};
+
+// ---------------------------------------------------------------------------
+// numpy-compatible helpers
+// ---------------------------------------------------------------------------
+// numpy binary_search_with_guess semantics (numpy/_core/src/multiarray/compiled_base.c):
+//  -1: x < xp[0]; n: x > xp[n-1]; n-1: x == xp[n-1]; else j with xp[j] <= x < xp[j+1]
+__device__ __forceinline__ int np_bin(const double* __restrict__ xp, int n, double x) {
+    if (x < xp[0]) return -1;
+    if (x > xp[n - 1]) return n;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (xp[hi] <= x) return hi;
+    return lo;
+}
+
+// general branch of numpy arr_interp: slope*(x-x0)+f0 with the NaN rescue
+__device__ __forceinline__ double np_lerp(double x, double x0, double x1, double f0, double f1) {
+    double slope = (f1 - f0) / (x1 - x0);
+    double r = slope * (x - x0) + f0;
+    if (isnan(r)) {
+        r = slope * (x - x1) + f1;
+        if (isnan(r) && f0 == f1) r = f0;
+    }
+    return r;
+}
+
+__device__ __forceinline__ double np_interp_at(double x, const double* __restrict__ xp,
+                                               const double* __restrict__ fp, int n, double left,
+                                               double right) {
+    if (isnan(x)) return x;
+    int j = np_bin(xp, n, x);
+    if (j < 0) return left;
+    if (j >= n) return right;
+    if (j == n - 1) return fp[j];
+    if (xp[j] == x) return fp[j];
+    return np_lerp(x, xp[j], xp[j + 1], fp[j], fp[j + 1]);
+}
+
+// np.nan_to_num for a scalar
+__device__ __forceinline__ double nan_to_num(double v) {
+    if (isnan(v)) return 0.0;
+    if (isinf(v)) return v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    return v;
+}
+
+// utils/find_nearest_index.py:33  (np.abs(arr - value)).argmin(), first minimum.
+// wl is ascending, so |wl - v| is V-shaped: candidates are the two neighbours
+// of the insertion point; equal-distance runs resolve to the lowest index.
+__device__ int nearest_index(const double* __restrict__ wl, int n, double v) {
+    if (isnan(v)) return 0;   // argmin of all-NaN is 0
+    int lo = 0, hi = n;       // first index with wl[i] >= v
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (wl[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int c = lo;
+    if (c >= n) c = n - 1;
+    if (c > 0 && fabs(wl[c - 1] - v) <= fabs(wl[c] - v)) c = c - 1;
+    while (c > 0 && fabs(wl[c - 1] - v) == fabs(wl[c] - v)) --c;
+    return c;
+}
+
+// reciprocal to ~1 ulp: MUFU.RCP64H seed + two Newton steps (4 DFMA), no
+// special-case slow path (arguments here are products of (dl^2 + w^2) terms,
+// always normal and positive)
+__device__ __forceinline__ double rcp_fast(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+// ---------------------------------------------------------------------------
+// setup kernels (plan creation)
+// ---------------------------------------------------------------------------
+// log_conv resampling operator (BC:218-241): bins of the two np.interp calls
+__global__ void k_bc_bins(int P, const double* __restrict__ wl, const double* __restrict__ lnwl,
+                          const double* __restrict__ lnnew, const double* __restrict__ expnew,
+                          int* __restrict__ jA, int* __restrict__ kB) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    jA[i] = np_bin(expnew, P, wl[i]);      // np.interp(wavelength, exp(ln_wavenew), flux_conv)
+    kB[i] = np_bin(lnwl, P, lnnew[i]);     // np.interp(ln_wavenew, ln_wave, orig_flux)
+}
+
+// Gaussian broadening in ln-lambda space for a list of rows (template t, sigma_norm):
+//   kernel = signal.gaussian(K*sigma, sigma)/(sqrt(2 pi) sigma)          Fe:291-293 / HG:298-300
+//   conv   = np.convolve(log_flux, kernel, mode="same")                  Fe:304     / HG:311
+// One CTA = one row x one tile of kConvTile output points; the template tile
+// (+ halo) and the kernel taps are staged in shared memory.
+__global__ void __launch_bounds__(kConvTile)
+k_conv_rows(TemplDev ts, const int* __restrict__ row_t, const int* __restrict__ row_sig,
+            double* __restrict__ conv, int stride) {
+    extern __shared__ double smem[];
+    const int r = blockIdx.y;
+    const int t = row_t[r];
+    const int sig = row_sig[r];
+    const int N = ts.n_pts[t];
+    const int m0 = blockIdx.x * kConvTile;
+    if (m0 >= N) return;
+    double* out = conv + (size_t)r * stride;
+    if (sig < 1) {   // reference: empty kernel -> ValueError; we poison the row
+        int m = m0 + threadIdx.x;
+        if (m < N) out[m] = CUDART_NAN;
+        return;
+    }
+    const int M = ts.ksize * sig;
+    const int off = (M - 1) / 2;
+    double* kw = smem;            // [M]
+    double* gs = smem + M;        // [kConvTile + M - 1]
+    const double* g = ts.logf + ts.off[t];
+    const double sg = (double)sig;
+    const double sig2 = 2 * sg * sg;
+    const double nrm = ts.sqrt_2pi * sg;
+    const double half = ((double)M - 1.0) / 2.0;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        double n = (double)j - half;
+        kw[j] = exp(-(n * n) / sig2) / nrm;
+    }
+    // output m needs g[m + off - j], j = 0..M-1  ->  indices [m0+off-(M-1), m0+kConvTile-1+off]
+    const int lo = m0 + off - (M - 1);
+    const int span = kConvTile + M - 1;
+    for (int s = threadIdx.x; s < span; s += blockDim.x) {
+        int idx = lo + s;
+        gs[s] = (idx >= 0 && idx < N) ? g[idx] : 0.0;
+    }
+    __syncthreads();
+    const int m = m0 + threadIdx.x;
+    if (m >= N) return;
+    // gs index of g[m + off - j] = (m + off - j) - lo = threadIdx.x + (M-1) - j
+    double acc = 0.0;
+    const double* gp = gs + threadIdx.x + (M - 1);
+    for (int j = 0; j < M; ++j) acc = fma(gp[-j], kw[j], acc);
+    out[m] = acc;
+}
+
+// conv (ln-lambda grid) -> data grid:  np.interp(np.log(wl), log_wl, conv [,left=0,right=0])
+__global__ void k_interp_rows(TemplDev ts, const int* __restrict__ row_t,
+                              const double* __restrict__ conv, int stride,
+                              const double* __restrict__ lnwl, int P, double* __restrict__ frows) {
+    const int r = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int t = row_t[r];
+    const int N = ts.n_pts[t];
+    const double* xp = ts.logx + ts.off[t];
+    const double* fp = conv + (size_t)r * stride;
+    double left = ts.clamp ? fp[0] : 0.0;
+    double right = ts.clamp ? fp[N - 1] : 0.0;
+    frows[(size_t)r * P + i] = np_interp_at(lnwl[i], xp, fp, N, left, right);
+}
+
+// nf = np.nan_to_num(np.interp(median(template wl), wl, f))     Fe:325-331 / HG:330-336
+__global__ void k_norm_rows(TemplDev ts, const int* __restrict__ row_t, int n_rows,
+                            const double* __restrict__ wl, int P,
+                            const double* __restrict__ frows, double* __restrict__ nf) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const double* f = frows + (size_t)r * P;
+    double v = np_interp_at(ts.norm_wl[row_t[r]], wl, f, P, f[0], f[P - 1]);
+    nf[r] = nan_to_num(v);
+}
+
+// sigma_norm = np.ceil(sqrt(width^2 - templ_width^2)/(c_kms 2 sqrt(2 ln 2)) / bin)   Fe:285-290
+__device__ __forceinline__ double sigma_norm_of(const TemplDev& ts, int t, double width) {
+    double sc = sqrt(width * width - ts.templ_width * ts.templ_width) / ts.sigma_denom;
+    return ceil(sc / ts.bin[t]);
+}
+
+// rows for the direct mode: one row per (walker, template)
+__global__ void k_rows_from_params(TemplDev ts, const double* __restrict__ params, int D, int w0,
+                                   int nW, int* __restrict__ row_t, int* __restrict__ row_sig) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nW * ts.n_templ) return;
+    int w = idx / ts.n_templ, t = idx % ts.n_templ;
+    double width = params[(size_t)(w0 + w) * D + ts.param_off + ts.n_templ];
+    double sn = sigma_norm_of(ts, t, width);
+    int sig = (sn >= 1.0 && sn <= 1.0e6) ? (int)sn : 0;
+    row_t[idx] = t;
+    row_sig[idx] = sig;
+}
+
+// flag (device word) whether every walker's sigma_norm is inside the bank
+__global__ void k_check_bank(TemplDev ts, const double* __restrict__ params, int D, int nW,
+                             int* __restrict__ flag) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nW * ts.n_templ) return;
+    int w = idx / ts.n_templ, t = idx % ts.n_templ;
+    double width = params[(size_t)w * D + ts.param_off + ts.n_templ];
+    double sn = sigma_norm_of(ts, t, width);
+    if (!(sn >= 1.0 && sn <= (double)ts.bank_sig_max[t])) atomicOr(flag, 1);
+}
+
+// ---------------------------------------------------------------------------
+// the fused walker kernel
+// ---------------------------------------------------------------------------
+struct DirectRows {          // per-walker broadened templates (direct mode); null in bank mode
+    const double* fe_f;  const double* fe_nf;
+    const double* host_f; const double* host_nf;
+};
+
+struct TemplCoef {
+    const double* f;   // row on the data grid
+    double a;          // norm_t / nf
+};
+
+// Storey & Hummer table look-up: kx=ky=1 FITPACK spline == clamped bilinear
+__device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) {
+    double x = fmin(fmax(n_e, pl.sh_ne[0]), pl.sh_ne[SPAMM_SH95_NE - 1]);
+    double y = fmin(fmax(T, pl.sh_T[0]), pl.sh_T[SPAMM_SH95_T - 1]);
+    int i = 0, j = 0;
+    for (int q = 1; q < SPAMM_SH95_NE - 1; ++q) if (pl.sh_ne[q] <= x) i = q;
+    for (int q = 1; q < SPAMM_SH95_T - 1; ++q) if (pl.sh_T[q] <= y) j = q;
+    double tx = (x - pl.sh_ne[i]) / (pl.sh_ne[i + 1] - pl.sh_ne[i]);
+    double ty = (y - pl.sh_T[j]) / (pl.sh_T[j + 1] - pl.sh_T[j]);
+    const double* z = pl.sh_z + (size_t)k * SPAMM_SH95_NE * SPAMM_SH95_T;
+    double z00 = z[i * SPAMM_SH95_T + j], z10 = z[(i + 1) * SPAMM_SH95_T + j];
+    double z01 = z[i * SPAMM_SH95_T + j + 1], z11 = z[(i + 1) * SPAMM_SH95_T + j + 1];
+    return ((1 - tx) * (1 - ty) * z00 + tx * (1 - ty) * z10 + (1 - tx) * ty * z01) + tx * ty * z11;
+}
+
+// unnormalised Balmer continuum sample: (1 - exp(-tau)) * blackbody_lambda     BC:435-440
+__device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double tauBE) {
+    double log_boltz = pl.bc_hnu[k] / kT;
+    double boltzm1 = expm1(log_boltz);
+    double bnu = pl.bc_b1[k] / (pl.c_cgs2 * boltzm1);
+    double flam = bnu * pl.c_aa / pl.bc_lam2[k];
+    double tau = tauBE * pl.bc_t3[k];
+    double absorption = 1 - exp(-tau);
+    return absorption * flam;
+}
+
+// flux_rebin[j] = np.interp(ln_wavenew[j], ln_wave, f0)                         BC:225
+__device__ __forceinline__ double bc_fr(const PlanDev& pl, const double* __restrict__ f0s, int j) {
+    int k = pl.bc_kB[j];
+    if (k < 0) return f0s[0];
+    if (k >= pl.P - 1) return f0s[pl.P - 1];
+    double x = pl.bc_lnnew[j];
+    double x0 = pl.lnwl[k];
+    if (x0 == x) return f0s[k];
+    return np_lerp(x, x0, pl.lnwl[k + 1], f0s[k], f0s[k + 1]);
+}
+
+// log_conv output at data pixel i (kernel == [1.0], see k_lnpost prologue)     BC:239
+__device__ __forceinline__ double bc_conv_at(const PlanDev& pl, const double* __restrict__ f0s, int i) {
+    int j = pl.bc_jA[i];
+    if (j < 0) return bc_fr(pl, f0s, 0);
+    if (j >= pl.P - 1) return bc_fr(pl, f0s, pl.P - 1);
+    double x = pl.wl[i];
+    double x0 = pl.bc_expnew[j];
+    if (x0 == x) return bc_fr(pl, f0s, j);
+    return np_lerp(x, x0, pl.bc_expnew[j + 1], bc_fr(pl, f0s, j), bc_fr(pl, f0s, j + 1));
+}
+
+// highest f0 index bc_conv_at(i) touches
+__device__ __forceinline__ int bc_max_src(const PlanDev& pl, int i) {
+    int j = pl.bc_jA[i];
+    j = j < 0 ? 0 : (j >= pl.P - 1 ? pl.P - 1 : j + 1);
+    int k = pl.bc_kB[j];
+    k = k < 0 ? 0 : (k >= pl.P - 1 ? pl.P - 1 : k + 1);
+    return k;
+}
+
+struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
+    double p[kMaxDim];
+    TemplCoef fe[SPAMM_MAX_TEMPLATES];
+    TemplCoef host[SPAMM_MAX_TEMPLATES];
+    double red[kThreads / 32];
+    double nc_norm, nc_slope1, nc_slope2, nc_break;
+    double bc_scale, bpc_scale;      // normalization / fnorm
+    double kT, tauBE;
+    int bc_istar, bpc_istar;
+    int prior_ok;
+};
+
+static_assert(sizeof(WalkerCtx) % 16 == 0, "line table must stay 16-byte aligned");
+
+// cheap components of pixel i: NC + Fe + host, in Model.model_flux order (Model.py:353-364)
+__device__ __forceinline__ double cheap_flux(const PlanDev& pl, const WalkerCtx& c, uint32_t mask,
+                                             int i, double balmer, bool have_balmer) {
+    double m = 0.0;
+    for (int q = 0; q < pl.n_comp; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        int kind = pl.comp_kind[q];
+        if (kind == SPAMM_COMP_NUCLEAR) {
+            double v;
+            if (!pl.nc_broken) {
+                v = c.nc_norm * pow(pl.nc_x[i], -c.nc_slope1);                    // NC:195
+            } else {
+                double lam = pl.wl[i];
+                double alpha = lam < c.nc_break ? c.nc_slope1 : c.nc_slope2;      // NC:199
+                v = c.nc_norm * pow(lam / c.nc_break, -alpha);
+            }
+            m = m + v;
+        } else if (kind == SPAMM_COMP_FE) {
+            double s = 0.0;
+            for (int t = 0; t < pl.fe.n_templ; ++t) s = s + c.fe[t].a * c.fe[t].f[i];    // Fe:334
+            m = m + s;
+        } else if (kind == SPAMM_COMP_HOST) {
+            double s = 0.0;
+            for (int t = 0; t < pl.host.n_templ; ++t) s = s + c.host[t].a * c.host[t].f[i];  // HG:339
+            m = m + s;
+        } else if (kind == SPAMM_COMP_BALMER) {
+            if (have_balmer) m = m + balmer;
+        }
+    }
+    return m;
+}
+
+template <int MODE>   // 0: ln-posterior; 1: model flux out
+__global__ void __launch_bounds__(kThreads, 2)
+k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
+          uint32_t mask, DirectRows dr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WalkerCtx& c = *reinterpret_cast<WalkerCtx*>(smem_raw);
+    double* sLine = reinterpret_cast<double*>(smem_raw + sizeof(WalkerCtx));   // [3][n_lines_pad] grouped
+    double* sG = sLine + 3 * pl.n_lines_pad;                                    // [n_lines_pad]
+    double* sW = sG + pl.n_lines_pad;                                           // [n_lines_pad]
+    double* sF0 = sW + pl.n_lines_pad;                                          // [bc_nstage]
+
+    const int tid = threadIdx.x;
+    const int wloc = blockIdx.x;           // walker within this launch
+    const int w = w0 + wloc;
+    const int P = pl.P;
+    const double* pw = params + (size_t)w * pl.D;
+
+    // ---- parameters + flat-box prior (Model.prior, Model.py:449-470) -----------
+    if (tid == 0) c.prior_ok = 1;
+    __syncthreads();
+    if (tid < pl.D) {
+        double v = pw[tid];
+        c.p[tid] = v;
+        if (MODE == 0 && pl.lo != nullptr) {
+            if (!(pl.lo[tid] < v && v < pl.hi[tid])) c.prior_ok = 0;   // strict; NaN fails
+        }
+    }
+    __syncthreads();
+    if (MODE == 0 && !c.prior_ok) {       // ln_posterior returns -inf before any flux (Model.py:67-69)
+        if (tid == 0) out[w] = -CUDART_INF;
+        return;
+    }
+
+    // ---- which components are live ----------------------------------------------
+    int off_nc = -1, off_bal = -1;
+    bool has_fe = false, has_host = false;
+    for (int q = 0; q < pl.n_comp; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        int kind = pl.comp_kind[q];
+        if (kind == SPAMM_COMP_NUCLEAR) off_nc = pl.comp_off[q];
+        else if (kind == SPAMM_COMP_FE) has_fe = true;
+        else if (kind == SPAMM_COMP_HOST) has_host = true;
+        else if (kind == SPAMM_COMP_BALMER) off_bal = pl.comp_off[q];
+    }
+    const bool do_bc = off_bal >= 0 && pl.bc_on;
+    const bool do_bpc = off_bal >= 0 && pl.bpc_on;
+
+    // ---- per-walker scalars --------------------------------------------------------
+    if (tid == 0 && off_nc >= 0) {
+        if (!pl.nc_broken) {
+            c.nc_norm = c.p[off_nc]; c.nc_slope1 = c.p[off_nc + 1];
+            c.nc_slope2 = 0; c.nc_break = 0;
+        } else {
+            c.nc_break = c.p[off_nc]; c.nc_norm = c.p[off_nc + 1];
+            c.nc_slope1 = c.p[off_nc + 2]; c.nc_slope2 = c.p[off_nc + 3];
+        }
+    }
+    // template rows + coefficients: thread t of warp 1 (Fe) / warp 2 (host)
+    if (has_fe && tid >= 32 && tid < 32 + pl.fe.n_templ) {
+        const TemplDev& ts = pl.fe;
+        int t = tid - 32;
+        double norm = c.p[ts.param_off + t];
+        const double* f; double nf;
+        if (dr.fe_f != nullptr) {
+            size_t row = (size_t)wloc * ts.n_templ + t;
+            f = dr.fe_f + row * P; nf = dr.fe_nf[row];
+        } else {
+            double sn = sigma_norm_of(ts, t, c.p[ts.param_off + ts.n_templ]);
+            int sig = 1;
+            if (sn >= 1.0 && sn <= (double)ts.bank_sig_max[t]) sig = (int)sn;
+            else { atomicOr(pl.status, kStatSigmaRange); norm = CUDART_NAN; }
+            int row = ts.bank_row0[t] + sig - 1;
+            f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
+        }
+        c.fe[t].f = f;
+        c.fe[t].a = norm / nf;                                          // Fe:334
+    }
+    if (has_host && tid >= 64 && tid < 64 + pl.host.n_templ) {
+        const TemplDev& ts = pl.host;
+        int t = tid - 64;
+        double norm = c.p[ts.param_off + t];
+        const double* f; double nf;
+        if (dr.host_f != nullptr) {
+            size_t row = (size_t)wloc * ts.n_templ + t;
+            f = dr.host_f + row * P; nf = dr.host_nf[row];
+        } else {
+            double sn = sigma_norm_of(ts, t, c.p[ts.param_off + ts.n_templ]);
+            int sig = 1;
+            if (sn >= 1.0 && sn <= (double)ts.bank_sig_max[t]) sig = (int)sn;
+            else { atomicOr(pl.status, kStatSigmaRange); norm = CUDART_NAN; }
+            int row = ts.bank_row0[t] + sig - 1;
+            f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
+        }
+        c.host[t].f = f;
+        c.host[t].a = norm / nf;                                        // HG:339
+    }
+
+    // ---- Balmer prologue ---------------------------------------------------------------
+    double b_norm = 0, b_Te = 0, b_tau = 0, b_loff = 0, b_lwid = 0, b_logNe = 0;
+    if (off_bal >= 0) {
+        b_norm = c.p[off_bal]; b_Te = c.p[off_bal + 1]; b_tau = c.p[off_bal + 2];
+        b_loff = c.p[off_bal + 3]; b_lwid = c.p[off_bal + 4]; b_logNe = c.p[off_bal + 5];
+    }
+    const int n_lines = pl.n_lines, n_pad = pl.n_lines_pad;
+    if (do_bpc) {
+        const double shift = b_loff / pl.c_kms;          // BC:379
+        const double width = b_lwid / pl.c_kms;
+        const double n_e = pow(10.0, b_logNe);           // BC:376
+        const double kT = pl.kb * b_Te;                  // k.value*T, BC:296
+        for (int n = tid; n < n_pad; n += kThreads) {
+            double lc = 0.0, wv = 0.0, rg = 0.0;
+            if (n < n_lines) {
+                double c0 = pl.line_c0[n];
+                lc = c0 - shift * c0;                    // lcenter -= shift*lcenter, BC:314
+                wv = width * lc;                         // BC:316
+                int nn = pl.line_min + n;
+                if (nn <= 50) rg = sh95_bilinear(pl, 50 - nn, n_e, b_Te);   // coef_use[-i+2], BC:294
+                else rg = exp(pl.line_e[n] / kT);                            // BC:296
+            }
+            sLine[(n >> 2) * 12 + (n & 3)] = lc;
+            sW[n] = wv;
+            sG[n] = rg;      // ratio (n <= 50) or the recursion factor (n > 50)
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // flux_ratios[i] = flux_ratios[i-1] * exp(...)  sequentially, BC:292-296
+            double prev = 0.0;    // flux_ratios[-1] of the zero-initialised array
+            for (int n = 0; n < n_lines; ++n) {
+                if (pl.line_min + n <= 50) prev = sG[n];
+                else { prev = prev * sG[n]; sG[n] = prev; }
+            }
+        }
+        __syncthreads();
+        for (int n = tid; n < n_pad; n += kThreads) {
+            int gq = n >> 2, r4 = n & 3;
+            double wv = sW[n], rr = sG[n];
+            if (n < n_lines) {
+                sLine[gq * 12 + 4 + r4] = wv * wv;
+                sLine[gq * 12 + 8 + r4] = (pl.line_type == SPAMM_LINE_LORENTZIAN) ? rr * wv : rr;
+            } else {   // padding: contributes exactly 0
+                sLine[gq * 12 + 4 + r4] = 1.0;
+                sLine[gq * 12 + 8 + r4] = 0.0;
+            }
+        }
+    }
+    if (tid == 0) {
+        c.bc_istar = -1; c.bpc_istar = -1; c.bc_scale = 0; c.bpc_scale = 0;
+        c.kT = pl.kb * b_Te; c.tauBE = b_tau;
+        if (do_bc) {
+            double edge_wl = pl.edge * (1 - b_loff / pl.c_cgs);          // BC:432 (cm/s!)
+            c.bc_istar = nearest_index(pl.wl, P, edge_wl);               // BC:443
+            // log_conv kernel: kernel_width = round(5*dpix) must be 0          BC:229-233
+            double dpix = (b_lwid / pl.c_cgs) / pl.bc_dlnew;
+            if (rint(5 * dpix) != 0.0) atomicOr(pl.status, kStatBcKernel);
+            if (bc_max_src(pl, c.bc_istar) >= pl.bc_nstage) atomicOr(pl.status, kStatBcStage);
+        }
+        if (do_bpc) {
+            double edge_wl = pl.edge * (1 - b_loff / pl.c_kms);          // BC:374
+            c.bpc_istar = nearest_index(pl.wl, P, edge_wl);              // BC:382
+        }
+    }
+    __syncthreads();
+
+    // ---- BC: stage f0 and normalise ---------------------------------------------------
+    if (do_bc) {
+        const double kT = c.kT, tauBE = c.tauBE;
+        int nst = min(pl.bc_nstage, P);
+        for (int k = tid; k < nst; k += kThreads) sF0[k] = bc_f0(pl, k, kT, tauBE);
+        __syncthreads();
+        if (tid == 0) {
+            double fnorm = bc_conv_at(pl, sF0, c.bc_istar);              // BC:444
+            c.bc_scale = b_norm / fnorm;                                 // BC:446
+        }
+    }
+    // ---- BpC normaliser: the line sum at the edge pixel (BC:385) -----------------------
+    if (do_bpc && tid < 32) {
+        const double lam = pl.wl[c.bpc_istar];
+        double s = 0.0;
+        for (int n = tid; n < n_lines; n += 32) {
+            int gq = n >> 2, r4 = n & 3;
+            double d = lam - sLine[gq * 12 + r4];
+            double w2 = sLine[gq * 12 + 4 + r4];
+            double a = sLine[gq * 12 + 8 + r4];
+            if (pl.line_type == SPAMM_LINE_LORENTZIAN) s += a / (d * d + w2);
+            else s += a * exp(-(d * d) / w2);
+        }
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) c.bpc_scale = b_norm / s;                          // BC:387
+    }
+    __syncthreads();
+
+    const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
+    const double bc_scale = c.bc_scale, bpc_scale = c.bpc_scale;
+    const bool have_balmer = off_bal >= 0;
+    double chi = 0.0;
+    double* fout = (MODE == 1) ? out + (size_t)wloc * P : nullptr;
+
+    // ---- loop A: pixels without line work (i <= bpc_istar, or everything if no BpC) -----
+    const int endA = do_bpc ? min(bpc_istar + 1, P) : P;
+    for (int i = tid; i < endA; i += kThreads) {
+        double balmer = 0.0;
+        if (have_balmer) {
+            double bc = 0.0, bpc = 0.0;
+            if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;   // BC:445-446
+            if (do_bpc) bpc = 0.0 * bpc_scale;                                              // BC:386-387
+            balmer = (do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc);                     // BC:462-471
+        }
+        double m = cheap_flux(pl, c, mask, i, balmer, have_balmer);
+        if (MODE == 0) {
+            double r = (pl.flux[i] - m) / pl.err[i];                                        // Model.py:440
+            chi += r * r;
+        } else {
+            fout[i] = m;
+        }
+    }
+
+    // ---- loop B: pixels redward of the edge: 397-line sum ---------------------------------
+    if (do_bpc) {
+        const int n_groups = n_pad >> 2;
+        const double2* sL2 = reinterpret_cast<const double2*>(sLine);
+        for (int base = endA; base < P; base += kThreads * kPix) {
+            double lam[kPix], acc[kPix];
+            int idx[kPix];
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) {
+                idx[q] = base + q * kThreads + tid;
+                lam[q] = pl.wl[min(idx[q], P - 1)];
+                acc[q] = 0.0;
+            }
+            if (base + (tid & ~31) < P) {     // warp has at least one live pixel in slot 0
+                if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
+#pragma unroll 1
+                    for (int g = 0; g < n_groups; ++g) {
+                        const double2 c01 = sL2[g * 6 + 0], c23 = sL2[g * 6 + 1];
+                        const double2 w01 = sL2[g * 6 + 2], w23 = sL2[g * 6 + 3];
+                        const double2 a01 = sL2[g * 6 + 4], a23 = sL2[g * 6 + 5];
+#pragma unroll
+                        for (int q = 0; q < kPix; ++q) {
+                            // four Lorentzians a/(d^2+w^2) over one common denominator
+                            double d0 = lam[q] - c01.x, d1 = lam[q] - c01.y;
+                            double d2 = lam[q] - c23.x, d3 = lam[q] - c23.y;
+                            double x0 = fma(d0, d0, w01.x), x1 = fma(d1, d1, w01.y);
+                            double x2 = fma(d2, d2, w23.x), x3 = fma(d3, d3, w23.y);
+                            double p01 = x0 * x1, p23 = x2 * x3;
+                            double n01 = fma(a01.x, x1, a01.y * x0);
+                            double n23 = fma(a23.x, x3, a23.y * x2);
+                            double num = fma(n01, p23, n23 * p01);
+                            double den = p01 * p23;
+                            acc[q] = fma(num, rcp_fast(den), acc[q]);
+                        }
+                    }
+                } else {
+                    for (int n = 0; n < n_lines; ++n) {
+                        int gq = n >> 2, r4 = n & 3;
+                        double lc = sLine[gq * 12 + r4], w2 = sLine[gq * 12 + 4 + r4];
+                        double rr = sLine[gq * 12 + 8 + r4];
+#pragma unroll
+                        for (int q = 0; q < kPix; ++q) {
+                            double d = lam[q] - lc;
+                            acc[q] = fma(rr, exp(-(d * d) / w2), acc[q]);                   // BC:319
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) {
+                int i = idx[q];
+                if (i >= P) continue;
+                double bpc = acc[q] * bpc_scale;                                            // BC:387
+                double bc = 0.0;
+                if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;
+                double balmer = do_bc ? bc + bpc : bpc;
+                double m = cheap_flux(pl, c, mask, i, balmer, true);
+                if (MODE == 0) {
+                    double r = (pl.flux[i] - m) / pl.err[i];
+                    chi += r * r;
+                } else {
+                    fout[i] = m;
+                }
+            }
+        }
+    }
+
+    // ---- per-walker reduction + likelihood (Model.py:440-445) ---------------------------------
+    if (MODE == 0) {
+        for (int o = 16; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
+        if ((tid & 31) == 0) c.red[tid >> 5] = chi;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int q = 0; q < kThreads / 32; ++q) s += c.red[q];
+            double ln_l = -0.5 * (s + pl.sum_ln);
+            out[w] = nan_to_num(ln_l) + 0.0;      // + ln_prior (== 0 inside the box)
+        }
+    }
+}
+
+// Model.likelihood (Model.py:418-445) on a materialised [W][P] model flux
+__global__ void __launch_bounds__(kThreads)
+k_likelihood(const PlanDev pl, const double* __restrict__ model, double* __restrict__ out) {
+    __shared__ double red[kThreads / 32];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const double* m = model + (size_t)w * pl.P;
+    double chi = 0.0;
+    for (int i = tid; i < pl.P; i += kThreads) {
+        double r = (pl.flux[i] - m[i]) / pl.err[i];
+        chi += r * r;
+    }
+    for (int o = 16; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
+    if ((tid & 31) == 0) red[tid >> 5] = chi;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int q = 0; q < kThreads / 32; ++q) s += red[q];
+        out[w] = nan_to_num(-0.5 * (s + pl.sum_ln));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sampler kernels (emcee 2.2.1 stretch move)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                           uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// uniform in [0,1) with 53 bits
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+    uint64_t v = ((uint64_t)a << 32) | b;
+    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void k_stretch_propose(const double* __restrict__ walkers, int K, int D, int half,
+                                  double a, uint64_t seed, uint64_t iter, double* __restrict__ q,
+                                  double* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int Ns = K / 2;
+    if (i >= Ns) return;
+    uint32_t r[4];
+    philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)half,
+               (uint32_t)iter, (uint32_t)(iter >> 32) ^ 0x50524f50u, r);
+    double u = u53(r[0], r[1]);
+    double zz = ((a - 1.0) * u + 1.0);
+    zz = zz * zz / a;
+    int Nc = K - Ns;
+    int rint_ = (int)(u53(r[2], r[3]) * Nc);
+    if (rint_ >= Nc) rint_ = Nc - 1;
+    const double* s = walkers + (size_t)(half == 0 ? i : Ns + i) * D;
+    const double* cc = walkers + (size_t)(half == 0 ? Ns + rint_ : rint_) * D;
+    for (int d = 0; d < D; ++d) q[(size_t)i * D + d] = cc[d] - zz * (cc[d] - s[d]);
+    z[i] = zz;
+}
+
+__global__ void k_stretch_accept(double* __restrict__ walkers, double* __restrict__ lnp, int K,
+                                 int D, int half, const double* __restrict__ q,
+                                 const double* __restrict__ z, const double* __restrict__ lnp_q,
+                                 uint64_t seed, uint64_t iter, long long* __restrict__ nacc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int Ns = K / 2;
+    if (i >= Ns) return;
+    uint32_t r[4];
+    philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)half,
+               (uint32_t)iter, (uint32_t)(iter >> 32) ^ 0x41434350u, r);
+    double u = u53(r[0], r[1]);
+    int wi = half == 0 ? i : Ns + i;
+    double lnpdiff = ((double)D - 1.0) * log(z[i]) + lnp_q[i] - lnp[wi];
+    if (lnpdiff > log(u)) {
+        for (int d = 0; d < D; ++d) walkers[(size_t)wi * D + d] = q[(size_t)i * D + d];
+        lnp[wi] = lnp_q[i];
+        if (nacc) nacc[wi] += 1;
+    }
+}
+
+__global__ void k_chain_record(const double* __restrict__ walkers, const double* __restrict__ lnp,
+                               int K, int D, long long iter, long long n_iter,
+                               double* __restrict__ chain, double* __restrict__ lnp_chain) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    if (chain)
+        for (int d = 0; d < D; ++d) chain[((size_t)i * n_iter + iter) * D + d] = walkers[(size_t)i * D + d];
+    if (lnp_chain) lnp_chain[(size_t)i * n_iter + iter] = lnp[i];
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA peak probe
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_probe(int iters, double* sink) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9;
+    double a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+    const double m = 0.999999999, b = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) sink[0] = s;
+}
+
+// ---------------------------------------------------------------------------
+// host side: the plan
+// ---------------------------------------------------------------------------
+struct SpammPlan {
+    PlanDev dev{};
+    std::vector<void*> allocs;
+    int template_mode = SPAMM_TEMPLATES_BANK;
+    int bank_rows = 0;
+    int max_walkers = 0;
+    int n_sm = 148;
+    size_t smem_bytes = 0;
+    int64_t launches = 0;
+    bool has_data = false;
+    // direct-mode workspace
+    int direct_chunk = 0;
+    double *d_conv = nullptr, *d_fe_f = nullptr, *d_fe_nf = nullptr, *d_host_f = nullptr, *d_host_nf = nullptr;
+    int *d_row_t = nullptr, *d_row_sig = nullptr;
+    int conv_stride = 0;
+    int* d_flag = nullptr;
+    // host staging for the *_host entry point
+    double *h_params = nullptr, *h_lnp = nullptr, *d_params = nullptr, *d_lnp = nullptr;
+    cudaStream_t own_stream = nullptr;
+    int max_sigma_seen = 0;
+};
+
+template <typename T>
+static int upload(SpammPlan* pl, const T* host, size_t n, const T** dev_out) {
+    T* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    pl->allocs.push_back(d);
+    if (n) CUDA_TRY(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = d;
+    return SPAMM_OK;
+}
+
+template <typename T>
+static int dalloc(SpammPlan* pl, size_t n, T** dev_out) {
+    T* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    pl->allocs.push_back(d);
+    *dev_out = d;
+    return SPAMM_OK;
+}
+
+static int conv_smem_bytes(int ksize, int max_sigma) {
+    int M = ksize * max_sigma;
+    return (M + kConvTile + M - 1) * (int)sizeof(double);
+}
+
+// run the broadening pipeline for n_rows rows -> frows[n_rows][P], nf[n_rows]
+static int run_rows(SpammPlan* pl, const TemplDev& ts, const int* d_row_t, const int* d_row_sig,
+                    int n_rows, int max_sigma, double* d_conv, int stride, double* d_frows,
+                    double* d_nf, cudaStream_t st) {
+    if (n_rows == 0) return SPAMM_OK;
+    int smem = conv_smem_bytes(ts.ksize, std::max(max_sigma, 1));
+    if (smem > 200 * 1024)
+        return set_error(SPAMM_ERANGE, "broadening kernel too wide for shared memory");
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_conv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int nmax = 0;
+    for (int t = 0; t < ts.n_templ; ++t) nmax = std::max(nmax, ts.n_pts[t]);
+    dim3 g1((nmax + kConvTile - 1) / kConvTile, n_rows);
+    k_conv_rows<<<g1, kConvTile, smem, st>>>(ts, d_row_t, d_row_sig, d_conv, stride);
+    dim3 g2((pl->dev.P + 255) / 256, n_rows);
+    k_interp_rows<<<g2, 256, 0, st>>>(ts, d_row_t, d_conv, stride, pl->dev.lnwl, pl->dev.P, d_frows);
+    k_norm_rows<<<(n_rows + 127) / 128, 128, 0, st>>>(ts, d_row_t, n_rows, pl->dev.wl, pl->dev.P,
+                                                       d_frows, d_nf);
+    pl->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return SPAMM_OK;
+}
+
+static double host_sigma_norm(const SpammTemplateSet& s, double bin, double width) {
+    volatile double a = width * width;
+    volatile double b = s.template_width * s.template_width;
+    volatile double sc = std::sqrt(a - b) / s.sigma_denom;
+    return std::ceil(sc / bin);
+}
+
+static int setup_template_set(SpammPlan* pl, const SpammTemplateSet& src, int param_off,
+                              double width_hi, bool want_bank, TemplDev* out, bool* bank_ok) {
+    TemplDev ts{};
+    ts.n_templ = src.n_templates;
+    if (ts.n_templ < 1 || ts.n_templ > SPAMM_MAX_TEMPLATES)
+        return set_error(SPAMM_EINVAL, "template count out of range");
+    size_t total = 0;
+    for (int t = 0; t < ts.n_templ; ++t) {
+        if (src.n_points[t] < 3) return set_error(SPAMM_EINVAL, "template needs >= 3 points");
+        ts.n_pts[t] = src.n_points[t];
+        ts.off[t] = (int)total;
+        // bin_size = log grid [2] - [1]                                       Fe:288 / HG:295
+        ts.bin[t] = src.log_wl[total + 2] - src.log_wl[total + 1];
+        ts.norm_wl[t] = src.norm_wl[t];
+        total += src.n_points[t];
+    }
+    ts.templ_width = src.template_width;
+    ts.sigma_denom = src.sigma_denom;
+    ts.sqrt_2pi = src.sqrt_2pi;
+    ts.ksize = src.kernel_size_sigma;
+    ts.clamp = src.clamp_edges;
+    ts.param_off = param_off;
+    int rc;
+    if ((rc = upload(pl, src.log_wl, total, &ts.logx))) return rc;
+    if ((rc = upload(pl, src.log_flux, total, &ts.logf))) return rc;
+    for (int t = 0; t < ts.n_templ; ++t) pl->conv_stride = std::max(pl->conv_stride, ts.n_pts[t]);
+
+    *bank_ok = false;
+    if (want_bank && std::isfinite(width_hi)) {
+        int rows = 0;
+        bool ok = true;
+        for (int t = 0; t < ts.n_templ; ++t) {
+            double sn = host_sigma_norm(src, ts.bin[t], width_hi);
+            if (!(sn >= 1.0) || sn > 512.0) { ok = false; break; }
+            ts.bank_row0[t] = rows;
+            ts.bank_sig_max[t] = (int)sn;
+            rows += (int)sn;
+        }
+        if (ok && (size_t)rows * pl->dev.P * sizeof(double) <= ((size_t)2 << 30)) {
+            std::vector<int> rt(rows), rs(rows);
+            int max_sigma = 0;
+            for (int t = 0; t < ts.n_templ; ++t)
+                for (int s = 1; s <= ts.bank_sig_max[t]; ++s) {
+                    rt[ts.bank_row0[t] + s - 1] = t;
+                    rs[ts.bank_row0[t] + s - 1] = s;
+                    max_sigma = std::max(max_sigma, s);
+                }
+            const int *d_rt, *d_rs;
+            if ((rc = upload(pl, rt.data(), rows, &d_rt))) return rc;
+            if ((rc = upload(pl, rs.data(), rows, &d_rs))) return rc;
+            double *d_conv, *d_f, *d_nf;
+            int stride = 0;
+            for (int t = 0; t < ts.n_templ; ++t) stride = std::max(stride, ts.n_pts[t]);
+            CUDA_TRY(cudaMalloc(&d_conv, (size_t)rows * stride * sizeof(double)));
+            if ((rc = dalloc(pl, (size_t)rows * pl->dev.P, &d_f))) { cudaFree(d_conv); return rc; }
+            if ((rc = dalloc(pl, (size_t)rows, &d_nf))) { cudaFree(d_conv); return rc; }
+            rc = run_rows(pl, ts, d_rt, d_rs, rows, max_sigma, d_conv, stride, d_f, d_nf, 0);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaFree(d_conv);
+            if (rc) return rc;
+            if (e != cudaSuccess) return set_error(SPAMM_ECUDA, cudaGetErrorString(e));
+            ts.bank_f = d_f;
+            ts.bank_nf = d_nf;
+            pl->bank_rows += rows;
+            *bank_ok = true;
+        }
+    }
+    *out = ts;
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_abi_version(void) { return SPAMM_ABI_VERSION; }
+extern "C" const char* spamm_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" void spamm_plan_destroy(SpammPlan* pl) {
+    if (!pl) return;
+    for (void* p : pl->allocs) cudaFree(p);
+    cudaFree(pl->d_conv); cudaFree(pl->d_fe_f); cudaFree(pl->d_fe_nf);
+    cudaFree(pl->d_host_f); cudaFree(pl->d_host_nf); cudaFree(pl->d_row_t); cudaFree(pl->d_row_sig);
+    cudaFree(pl->d_params); cudaFree(pl->d_lnp);
+    if (pl->h_params) cudaFreeHost(pl->h_params);
+    if (pl->h_lnp) cudaFreeHost(pl->h_lnp);
+    if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
+    delete pl;
+}
+
+static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
+    if (d->abi_version != SPAMM_ABI_VERSION) return set_error(SPAMM_EINVAL, "ABI version mismatch");
+    const int P = d->n_pix;
+    if (P < 3 || !d->wl || !d->ln_wl) return set_error(SPAMM_EINVAL, "need n_pix >= 3, wl and ln_wl");
+    for (int i = 1; i < P; ++i)
+        if (!(d->wl[i] > d->wl[i - 1]))
+            return set_error(SPAMM_EINVAL, "wl must be strictly ascending");
+    if (d->n_components < 1 || d->n_components > SPAMM_MAX_COMPONENTS)
+        return set_error(SPAMM_EINVAL, "n_components out of range");
+    if (d->n_dim < 1 || d->n_dim > kMaxDim) return set_error(SPAMM_EINVAL, "n_dim out of range");
+    if (d->max_walkers < 1) return set_error(SPAMM_EINVAL, "max_walkers must be >= 1");
+
+    int dev_id = 0;
+    CUDA_TRY(cudaGetDevice(&dev_id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev_id));
+    pl->n_sm = prop.multiProcessorCount;
+    pl->max_walkers = d->max_walkers;
+
+    PlanDev& pd = pl->dev;
+    pd.P = P;
+    pd.D = d->n_dim;
+    int rc;
+    if ((rc = upload(pl, d->wl, P, &pd.wl))) return rc;
+    if ((rc = upload(pl, d->ln_wl, P, &pd.lnwl))) return rc;
+    pl->has_data = d->flux && d->flux_error;
+    if (pl->has_data) {
+        if ((rc = upload(pl, d->flux, P, &pd.flux))) return rc;
+        if ((rc = upload(pl, d->flux_error, P, &pd.err))) return rc;
+    }
+    pd.sum_ln = d->sum_ln_2pi_err2;
+    if (d->prior_lo && d->prior_hi) {
+        if ((rc = upload(pl, d->prior_lo, d->n_dim, &pd.lo))) return rc;
+        if ((rc = upload(pl, d->prior_hi, d->n_dim, &pd.hi))) return rc;
+    }
+    if ((rc = dalloc(pl, 1, &pd.status))) return rc;
+    CUDA_TRY(cudaMemset(pd.status, 0, sizeof(int)));
+    if ((rc = dalloc(pl, 1, &pl->d_flag))) return rc;
+
+    // component layout
+    pd.n_comp = d->n_components;
+    int off = 0, seen[4] = {0, 0, 0, 0};
+    int off_fe = -1, off_host = -1;
+    for (int q = 0; q < d->n_components; ++q) {
+        int kind = d->component_kind[q];
+        if (kind < 0 || kind > 3) return set_error(SPAMM_EINVAL, "unknown component kind");
+        if (seen[kind]++) return set_error(SPAMM_EINVAL, "each component kind may appear once");
+        pd.comp_kind[q] = kind;
+        pd.comp_off[q] = off;
+        if (kind == SPAMM_COMP_NUCLEAR) off += d->nc_broken_pl ? 4 : 2;
+        else if (kind == SPAMM_COMP_FE) { off_fe = off; off += d->fe.n_templates + 1; }
+        else if (kind == SPAMM_COMP_HOST) { off_host = off; off += d->host.n_templates + 1; }
+        else off += 6;
+    }
+    if (off != d->n_dim) return set_error(SPAMM_EINVAL, "n_dim does not match the component list");
+
+    // NC: wl / norm_wl   (PowerLaw1D: x / x_0)
+    pd.nc_broken = d->nc_broken_pl;
+    if (seen[SPAMM_COMP_NUCLEAR]) {
+        std::vector<double> x(P);
+        for (int i = 0; i < P; ++i) x[i] = d->wl[i] / d->nc_norm_wl;
+        if ((rc = upload(pl, x.data(), P, &pd.nc_x))) return rc;
+    }
+
+    // templates
+    bool want_bank = d->template_mode != SPAMM_TEMPLATES_DIRECT;
+    bool all_bank = true;
+    if (seen[SPAMM_COMP_FE]) {
+        bool ok = false;
+        double hi = d->prior_hi ? d->prior_hi[off_fe + d->fe.n_templates] : INFINITY;
+        if ((rc = setup_template_set(pl, d->fe, off_fe, hi, want_bank, &pd.fe, &ok))) return rc;
+        all_bank = all_bank && ok;
+    }
+    if (seen[SPAMM_COMP_HOST]) {
+        bool ok = false;
+        double hi = d->prior_hi ? d->prior_hi[off_host + d->host.n_templates] : INFINITY;
+        if ((rc = setup_template_set(pl, d->host, off_host, hi, want_bank, &pd.host, &ok))) return rc;
+        all_bank = all_bank && ok;
+    }
+    if (d->template_mode == SPAMM_TEMPLATES_BANK && !all_bank)
+        return set_error(SPAMM_EINVAL, "template bank requested but the width prior is unbounded/too wide");
+    pl->template_mode = (want_bank && all_bank) ? SPAMM_TEMPLATES_BANK : SPAMM_TEMPLATES_DIRECT;
+
+    // Balmer
+    pd.bc_on = d->balmer_bc;
+    pd.bpc_on = d->balmer_bpc;
+    pd.line_type = d->balmer_line_type;
+    pd.n_lines = 0;
+    pd.n_lines_pad = 0;
+    pd.bc_nstage = 0;
+    if (seen[SPAMM_COMP_BALMER]) {
+        if (!pd.bc_on && !pd.bpc_on)
+            return set_error(SPAMM_EINVAL, "BalmerCombined needs BalmerContinuum and/or BalmerPseudocContinuum");
+        pd.c_kms = d->c_kms; pd.c_cgs = d->c_cgs; pd.c_aa = d->c_aa;
+        pd.c_cgs2 = d->c_cgs * d->c_cgs;                      // c.cgs.value**2
+        pd.kb = d->kb_cgs; pd.edge = d->balmer_edge;
+        if (pd.bpc_on) {
+            if (d->balmer_line_min < 3) return set_error(SPAMM_EINVAL, "bc_lines_min must be >= 3");
+            if (d->balmer_n_lines < 1 || d->balmer_n_lines > kMaxLines)
+                return set_error(SPAMM_EINVAL, "number of Balmer lines out of range");
+            if (d->balmer_line_min <= 50 && !d->sh95_z) return set_error(SPAMM_EINVAL, "missing SH95 table");
+            pd.line_min = d->balmer_line_min;
+            pd.n_lines = d->balmer_n_lines;
+            pd.n_lines_pad = (pd.n_lines + 3) & ~3;
+            if ((rc = upload(pl, d->balmer_line_center, pd.n_lines, &pd.line_c0))) return rc;
+            if ((rc = upload(pl, d->balmer_line_exparg, pd.n_lines, &pd.line_e))) return rc;
+            memcpy(pd.sh_ne, d->sh95_ne, sizeof(pd.sh_ne));
+            memcpy(pd.sh_T, d->sh95_T, sizeof(pd.sh_T));
+            if (d->sh95_z)
+                if ((rc = upload(pl, d->sh95_z, (size_t)SPAMM_SH95_LINES * SPAMM_SH95_NE * SPAMM_SH95_T, &pd.sh_z)))
+                    return rc;
+        }
+        if (pd.bc_on) {
+            if (!d->bc_ln_wl_new || !d->bc_exp_ln_wl_new)
+                return set_error(SPAMM_EINVAL, "missing log_conv grids");
+            // walker-independent pieces of blackbody_lambda / tau, in the host's operation order
+            std::vector<double> hnu(P), b1(P), lam2(P), t3(P);
+            for (int i = 0; i < P; ++i) {
+                volatile double freq = d->c_aa / d->wl[i];               // c / lambda (AA/s / AA)
+                volatile double hn = d->h_cgs * freq;                     // h*freq
+                volatile double f3 = std::pow((double)freq, 3.0);         // freq ** 3
+                volatile double twoh = 2.0 * d->h_cgs;
+                hnu[i] = hn;
+                b1[i] = twoh * f3;                                        // 2 h freq^3
+                lam2[i] = d->wl[i] * d->wl[i];                            // lam ** 2
+                volatile double r = d->wl[i] / d->balmer_edge;
+                t3[i] = std::pow((double)r, 3.0);                         // (wl/balmer_edge)**3
+            }
+            if ((rc = upload(pl, hnu.data(), P, &pd.bc_hnu))) return rc;
+            if ((rc = upload(pl, b1.data(), P, &pd.bc_b1))) return rc;
+            if ((rc = upload(pl, lam2.data(), P, &pd.bc_lam2))) return rc;
+            if ((rc = upload(pl, t3.data(), P, &pd.bc_t3))) return rc;
+            if ((rc = upload(pl, d->bc_ln_wl_new, P, &pd.bc_lnnew))) return rc;
+            if ((rc = upload(pl, d->bc_exp_ln_wl_new, P, &pd.bc_expnew))) return rc;
+            pd.bc_dlnew = d->bc_ln_wl_new[1] - d->bc_ln_wl_new[0];
+            int *jA, *kB;
+            if ((rc = dalloc(pl, P, &jA))) return rc;
+            if ((rc = dalloc(pl, P, &kB))) return rc;
+            k_bc_bins<<<(P + 255) / 256, 256>>>(P, pd.wl, pd.lnwl, pd.bc_lnnew, pd.bc_expnew, jA, kB);
+            pl->launches += 1;
+            CUDA_TRY(cudaGetLastError());
+            std::vector<int> hjA(P), hkB(P);
+            CUDA_TRY(cudaMemcpy(hjA.data(), jA, P * sizeof(int), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(hkB.data(), kB, P * sizeof(int), cudaMemcpyDeviceToHost));
+            pd.bc_jA = jA; pd.bc_kB = kB;
+            // stage f0 up to the furthest source pixel of (nearest pixel to the edge) + 2
+            int ibe = 0;
+            double best = INFINITY;
+            for (int i = 0; i < P; ++i) {
+                double v = std::fabs(d->wl[i] - d->balmer_edge);
+                if (v < best) { best = v; ibe = i; }
+            }
+            int itop = std::min(ibe + 2, P - 1);
+            int j = hjA[itop];
+            j = j < 0 ? 0 : (j >= P - 1 ? P - 1 : j + 1);
+            int k = hkB[j];
+            k = k < 0 ? 0 : (k >= P - 1 ? P - 1 : k + 1);
+            pd.bc_nstage = std::min(P, k + 2);
+        }
+    }
+
+    // shared memory of the fused kernel
+    pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.bc_nstage) * sizeof(double);
+    if (pl->smem_bytes > 200 * 1024)
+        return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_plan_create(const SpammPlanDesc* desc, SpammPlan** out_plan) {
+    if (!desc || !out_plan) return set_error(SPAMM_EINVAL, "null argument");
+    SpammPlan* pl = new SpammPlan();
+    int rc = plan_create_impl(desc, pl);
+    if (rc) { spamm_plan_destroy(pl); *out_plan = nullptr; return rc; }
+    *out_plan = pl;
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_plan_n_dim(const SpammPlan* pl) { return pl ? pl->dev.D : SPAMM_EINVAL; }
+extern "C" int spamm_plan_n_pix(const SpammPlan* pl) { return pl ? pl->dev.P : SPAMM_EINVAL; }
+extern "C" int spamm_plan_template_mode(const SpammPlan* pl) { return pl ? pl->template_mode : SPAMM_EINVAL; }
+extern "C" int spamm_plan_bank_rows(const SpammPlan* pl) { return pl ? pl->bank_rows : SPAMM_EINVAL; }
+extern "C" int64_t spamm_plan_launch_count(const SpammPlan* pl) { return pl ? pl->launches : 0; }
+
+extern "C" int spamm_plan_status(SpammPlan* pl, void* stream) {
+    if (!pl) return set_error(SPAMM_EINVAL, "null plan");
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, pl->dev.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return h;
+}
+
+// direct-mode workspace (per-walker broadened rows), allocated on first use
+static int ensure_direct_ws(SpammPlan* pl) {
+    if (pl->direct_chunk) return SPAMM_OK;
+    const PlanDev& pd = pl->dev;
+    int nt = pd.fe.n_templ + pd.host.n_templ;
+    if (nt == 0) { pl->direct_chunk = pl->max_walkers; return SPAMM_OK; }
+    size_t per_walker = (size_t)nt * ((size_t)pd.P + pl->conv_stride) * sizeof(double);
+    size_t budget = (size_t)1 << 30;
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)pl->max_walkers, budget / per_walker));
+    int ntm = std::max(pd.fe.n_templ, pd.host.n_templ);
+    CUDA_TRY(cudaMalloc(&pl->d_conv, (size_t)chunk * ntm * pl->conv_stride * sizeof(double)));
+    if (pd.fe.n_templ) {
+        CUDA_TRY(cudaMalloc(&pl->d_fe_f, (size_t)chunk * pd.fe.n_templ * pd.P * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_fe_nf, (size_t)chunk * pd.fe.n_templ * sizeof(double)));
+    }
+    if (pd.host.n_templ) {
+        CUDA_TRY(cudaMalloc(&pl->d_host_f, (size_t)chunk * pd.host.n_templ * pd.P * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_host_nf, (size_t)chunk * pd.host.n_templ * sizeof(double)));
+    }
+    CUDA_TRY(cudaMalloc(&pl->d_row_t, (size_t)chunk * ntm * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&pl->d_row_sig, (size_t)chunk * ntm * sizeof(int)));
+    pl->direct_chunk = chunk;
+    return SPAMM_OK;
+}
+
+static int direct_rows_for_chunk(SpammPlan* pl, const TemplDev& ts, const double* params_dev, int w0,
+                                 int nW, double* d_f, double* d_nf, cudaStream_t st) {
+    int n_rows = nW * ts.n_templ;
+    k_rows_from_params<<<(n_rows + 127) / 128, 128, 0, st>>>(ts, params_dev, pl->dev.D, w0, nW,
+                                                               pl->d_row_t, pl->d_row_sig);
+    pl->launches += 1;
+    // the widest kernel decides the shared-memory size: read the sigmas back (direct mode is the
+    // cross-check path, not the throughput path)
+    std::vector<int> sig(n_rows);
+    CUDA_TRY(cudaMemcpyAsync(sig.data(), pl->d_row_sig, n_rows * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int max_sigma = 1;
+    for (int s : sig) max_sigma = std::max(max_sigma, s);
+    return run_rows(pl, ts, pl->d_row_t, pl->d_row_sig, n_rows, max_sigma, pl->d_conv, pl->conv_stride,
+                    d_f, d_nf, st);
+}
+
+template <int MODE>
+static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
+                          double* out_dev, cudaStream_t st, bool force_direct) {
+    const PlanDev& pd = pl->dev;
+    bool need_fe = false, need_host = false;
+    for (int q = 0; q < pd.n_comp; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        if (pd.comp_kind[q] == SPAMM_COMP_FE) need_fe = true;
+        if (pd.comp_kind[q] == SPAMM_COMP_HOST) need_host = true;
+    }
+    bool direct = (need_fe || need_host) && (force_direct || pl->template_mode == SPAMM_TEMPLATES_DIRECT);
+    if (!direct) {
+        DirectRows dr{nullptr, nullptr, nullptr, nullptr};
+        k_walkers<MODE><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr);
+        pl->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return SPAMM_OK;
+    }
+    int rc = ensure_direct_ws(pl);
+    if (rc) return rc;
+    for (int w0 = 0; w0 < n_walkers; w0 += pl->direct_chunk) {
+        int nW = std::min(pl->direct_chunk, n_walkers - w0);
+        DirectRows dr{nullptr, nullptr, nullptr, nullptr};
+        if (need_fe) {
+            if ((rc = direct_rows_for_chunk(pl, pd.fe, params_dev, w0, nW, pl->d_fe_f, pl->d_fe_nf, st))) return rc;
+            dr.fe_f = pl->d_fe_f; dr.fe_nf = pl->d_fe_nf;
+        }
+        if (need_host) {
+            if ((rc = direct_rows_for_chunk(pl, pd.host, params_dev, w0, nW, pl->d_host_f, pl->d_host_nf, st))) return rc;
+            dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
+        }
+        double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
+        k_walkers<MODE><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr);
+        pl->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SPAMM_OK;
+}
+
+static uint32_t full_mask(const SpammPlan* pl) { return (1u << pl->dev.n_comp) - 1u; }
+
+extern "C" int spamm_lnpost_batch(SpammPlan* pl, const double* params_dev, int32_t n_walkers,
+                                  double* lnp_dev, void* stream) {
+    if (!pl || !params_dev || !lnp_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_walkers < 0) return set_error(SPAMM_EINVAL, "negative walker count");
+    if (n_walkers == 0) return SPAMM_OK;
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, lnp_dev, (cudaStream_t)stream, false);
+}
+
+extern "C" int spamm_lnpost_batch_host(SpammPlan* pl, const double* params_host, int32_t n_walkers,
+                                       double* lnp_host) {
+    if (!pl || !params_host || !lnp_host) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_walkers < 0) return set_error(SPAMM_EINVAL, "negative walker count");
+    if (n_walkers == 0) return SPAMM_OK;
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    if (!pl->own_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&pl->own_stream, cudaStreamNonBlocking));
+        size_t np = (size_t)pl->max_walkers * pl->dev.D;
+        CUDA_TRY(cudaMallocHost(&pl->h_params, np * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&pl->h_lnp, (size_t)pl->max_walkers * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_params, np * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_lnp, (size_t)pl->max_walkers * sizeof(double)));
+    }
+    cudaStream_t st = pl->own_stream;
+    for (int w0 = 0; w0 < n_walkers; w0 += pl->max_walkers) {
+        int nW = std::min(pl->max_walkers, n_walkers - w0);
+        size_t nb = (size_t)nW * pl->dev.D * sizeof(double);
+        memcpy(pl->h_params, params_host + (size_t)w0 * pl->dev.D, nb);
+        CUDA_TRY(cudaMemcpyAsync(pl->d_params, pl->h_params, nb, cudaMemcpyHostToDevice, st));
+        int rc = launch_walkers<0>(pl, full_mask(pl), pl->d_params, nW, pl->d_lnp, st, false);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(pl->h_lnp, pl->d_lnp, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        memcpy(lnp_host + w0, pl->h_lnp, (size_t)nW * sizeof(double));
+    }
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_model_flux_batch(SpammPlan* pl, uint32_t mask, const double* params_dev,
+                                      int32_t n_walkers, double* flux_dev, void* stream) {
+    if (!pl || !params_dev || !flux_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_walkers < 0) return set_error(SPAMM_EINVAL, "negative walker count");
+    if (n_walkers == 0) return SPAMM_OK;
+    mask &= full_mask(pl);
+    if (!mask) return set_error(SPAMM_EINVAL, "empty component mask");
+    cudaStream_t st = (cudaStream_t)stream;
+    const PlanDev& pd = pl->dev;
+    // flux() may be called with widths the prior (and so the bank) never admits
+    bool force_direct = false;
+    if (pl->template_mode == SPAMM_TEMPLATES_BANK) {
+        CUDA_TRY(cudaMemsetAsync(pl->d_flag, 0, sizeof(int), st));
+        bool any = false;
+        for (int q = 0; q < pd.n_comp; ++q) {
+            if (!((mask >> q) & 1u)) continue;
+            const TemplDev* ts = pd.comp_kind[q] == SPAMM_COMP_FE ? &pd.fe
+                                 : pd.comp_kind[q] == SPAMM_COMP_HOST ? &pd.host : nullptr;
+            if (!ts) continue;
+            int n = n_walkers * ts->n_templ;
+            k_check_bank<<<(n + 127) / 128, 128, 0, st>>>(*ts, params_dev, pd.D, n_walkers, pl->d_flag);
+            pl->launches += 1;
+            any = true;
+        }
+        if (any) {
+            int h = 0;
+            CUDA_TRY(cudaMemcpyAsync(&h, pl->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            force_direct = h != 0;
+        }
+    }
+    return launch_walkers<1>(pl, mask, params_dev, n_walkers, flux_dev, st, force_direct);
+}
+
+extern "C" int spamm_likelihood_batch(SpammPlan* pl, const double* model_flux_dev, int32_t n_walkers,
+                                      double* lnl_dev, void* stream) {
+    if (!pl || !model_flux_dev || !lnl_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_walkers < 0) return set_error(SPAMM_EINVAL, "negative walker count");
+    if (n_walkers == 0) return SPAMM_OK;
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    k_likelihood<<<n_walkers, kThreads, 0, (cudaStream_t)stream>>>(pl->dev, model_flux_dev, lnl_dev);
+    pl->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return SPAMM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sampler + probe entry points
+// ---------------------------------------------------------------------------
+extern "C" int spamm_stretch_propose(const double* walkers_dev, int32_t K, int32_t D, int32_t half,
+                                     double a, uint64_t seed, uint64_t iteration, double* q_dev,
+                                     double* z_dev, void* stream) {
+    if (!walkers_dev || !q_dev || !z_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (K < 2 || (K & 1) || D < 1) return set_error(SPAMM_EINVAL, "need an even walker count");
+    int Ns = K / 2;
+    k_stretch_propose<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(walkers_dev, K, D, half, a, seed,
+                                                                          iteration, q_dev, z_dev);
+    CUDA_TRY(cudaGetLastError());
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_stretch_accept(double* walkers_dev, double* lnp_dev, int32_t K, int32_t D,
+                                    int32_t half, const double* q_dev, const double* z_dev,
+                                    const double* lnp_q_dev, uint64_t seed, uint64_t iteration,
+                                    int64_t* naccepted_dev, void* stream) {
+    if (!walkers_dev || !lnp_dev || !q_dev || !z_dev || !lnp_q_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (K < 2 || (K & 1) || D < 1) return set_error(SPAMM_EINVAL, "need an even walker count");
+    int Ns = K / 2;
+    k_stretch_accept<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed, iteration,
+        reinterpret_cast<long long*>(naccepted_dev));
+    CUDA_TRY(cudaGetLastError());
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_chain_record(const double* walkers_dev, const double* lnp_dev, int32_t K, int32_t D,
+                                  int64_t iter, int64_t n_iter, double* chain_dev, double* lnp_chain_dev,
+                                  void* stream) {
+    if (!walkers_dev || !lnp_dev) return set_error(SPAMM_EINVAL, "null argument");
+    k_chain_record<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(walkers_dev, lnp_dev, K, D, iter, n_iter,
+                                                                      chain_dev, lnp_chain_dev);
+    CUDA_TRY(cudaGetLastError());
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_fp64_peak_probe(int32_t iters, int32_t repeats, double* tflops_out) {
+    if (!tflops_out || iters < 1 || repeats < 1) return set_error(SPAMM_EINVAL, "bad argument");
+    int dev_id = 0;
+    CUDA_TRY(cudaGetDevice(&dev_id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev_id));
+    double* sink;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int blocks = prop.multiProcessorCount * 8;
+    k_dfma_probe<<<blocks, 256>>>(iters, sink);       // warm-up
+    double best = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_dfma_probe<<<blocks, 256>>>(iters, sink);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 8.0 * (double)iters * 256.0 * blocks;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    *tflops_out = best;
+    return SPAMM_OK;
+}

@@ -1,0 +1,229 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the
+reference-shaped Python plugin layer) against the golden vectors produced by
+the unmodified reference and against the numpy oracle on fresh seeded inputs.
+
+Tolerance: BASELINE.json north_star -- ln-posterior relative 1e-10 in FP64.
+Component fluxes are held to 1e-12 of the component's peak."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, Case, lnpost_cases, rel_err, grid, TRUTH
+
+pytestmark = pytest.mark.gpu
+
+LNPOST_RTOL = 1e-10
+FLUX_RTOL = 1e-12
+
+
+def _components(comps, bc=True, bpc=True, broken=False, line_type=None):
+    from spamm_b200.components.NuclearContinuumComponent import NuclearContinuumComponent
+    from spamm_b200.components.FeComponent import FeComponent
+    from spamm_b200.components.HostGalaxyComponent import HostGalaxyComponent
+    from spamm_b200.components.BalmerContinuumCombined import BalmerCombined
+    from spamm_b200.utils.parse_pars import parse_pars
+    out = []
+    for c in comps:
+        if c == "PL":
+            out.append(NuclearContinuumComponent(broken=broken))
+        elif c == "FE":
+            out.append(FeComponent())
+        elif c == "HOST":
+            out.append(HostGalaxyComponent())
+        elif c == "BC":
+            pars = parse_pars()["balmer_continuum"]
+            if line_type:
+                pars["bc_line_type"] = line_type
+            out.append(BalmerCombined(pars=pars, BalmerContinuum=bc, BalmerPseudocContinuum=bpc))
+    return out
+
+
+def _model(case, template_mode=None):
+    from spamm_b200.Model import Model
+    from spamm_b200.Spectrum import Spectrum
+    m = Model()
+    if template_mode is not None:
+        m.template_mode = template_mode
+    m.components += _components(case.comps, bc=case.bc, bpc=case.bpc)
+    m.data_spectrum = Spectrum(case.wl, case.flux, case.err)
+    return m
+
+
+def test_component_flux_vs_reference_golden():
+    from spamm_b200.Spectrum import Spectrum
+    z = np.load(os.path.join(GOLDEN, "components.npz"))
+    tags = sorted({tuple(k.split("/")[:2]) for k in z.files if k.count("/") == 2})
+    worst = {}
+    for gname, tag in tags:
+        wl = z["%s/wl" % gname]
+        params, flux = z["%s/%s/params" % (gname, tag)], z["%s/%s/flux" % (gname, tag)]
+        c = tag.split("_")[0]
+        comp = _components([c], bc="bcFalse" not in tag, bpc="bpcFalse" not in tag,
+                           broken="brokenTrue" in tag,
+                           line_type="gaussian" if "gaussian" in tag else None)[0]
+        sp = Spectrum(wl, wl, wl)
+        comp.initialize(sp)
+        got = comp.flux_batch(sp, params)
+        assert got.shape == flux.shape
+        err = np.max(np.abs(got - flux), axis=1) / np.max(np.abs(flux), axis=1)
+        worst[(gname, tag)] = err.max()
+        assert err.max() < FLUX_RTOL, (gname, tag, err)
+        # single-walker plugin call == row of the batched call (Component.flux API)
+        one = comp.flux(sp, list(params[0]))
+        assert np.array_equal(one, got[0])
+    print("worst component flux errors:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+
+
+@pytest.mark.parametrize("name", lnpost_cases()[1])
+def test_lnposterior_vs_reference_golden(name):
+    z, _ = lnpost_cases()
+    c = Case(z, name)
+    m = _model(c)
+    got = m.lnposterior_batch(c.params)
+    # the plan resolved the same prior boxes as the reference
+    assert np.array_equal(m.plan.lo, c.lo)
+    assert np.allclose(m.plan.hi, c.hi, rtol=1e-15, atol=0)
+    err = rel_err(got, c.lnpost)
+    assert err.max() < LNPOST_RTOL, (name, err.max())
+    assert np.array_equal(np.isneginf(got), np.isneginf(c.lnpost))
+    if name == "q6_fe_nan":
+        assert np.all(got == 0.0)            # NaN flux -> lnL == 0.0 (Model.py:443)
+    assert m.plan.status() == 0
+    # ln_posterior(new_params, model): the per-walker entry point emcee calls
+    from spamm_b200.Model import ln_posterior
+    assert ln_posterior(c.params[0], m) == got[0]
+
+
+def test_known_answer_pickle():
+    """The reference's own stored emcee chain + lnprob (examples/model.pickle.gz)."""
+    from spamm_b200.Model import Model
+    from spamm_b200.Spectrum import Spectrum
+    z = np.load(os.path.join(GOLDEN, "kat_pickle.npz"))
+    m = Model()
+    nc = _components(["PL"])[0]
+    nc.norm_min, nc.norm_max = float(z["lo"][0]), float(z["hi"][0])
+    nc.slope_min, nc.slope_max = float(z["lo"][1]), float(z["hi"][1])
+    m.components.append(nc)
+    m.data_spectrum = Spectrum(z["wl"], z["flux"], z["err"])
+    got = m.lnposterior_batch(z["params"])
+    assert rel_err(got, z["lnprob"]).max() < LNPOST_RTOL
+
+
+def test_lnposterior_vs_oracle_fresh_inputs():
+    """Seeded inputs the fixtures never saw, all four components, three grids."""
+    from oracle.spamm_numpy import OracleModel
+    rng = np.random.RandomState(99)
+    for P, W in ((1024, 48), (3000, 24)):
+        wl = np.sort(1000.0 + 9000.0 * rng.rand(P)) if P == 3000 else grid(P)
+        comps = ["PL", "FE", "HOST", "BC"]
+        o0 = OracleModel(wl, wl, wl, comps=comps)
+        fl = [o0.component_flux(c, TRUTH[c]) for c in comps]
+        d = np.sum(fl, axis=0) * (1 + 0.02 * rng.standard_normal(P))
+        e = np.sqrt(np.sum([(0.05 * f) ** 2 for f in fl], axis=0))
+        o = OracleModel(wl, d, e, comps=comps)
+        np.random.seed(7 + P)
+        params = np.array([o.initial_values() for _ in range(W)])
+        params[::5, 17] = rng.uniform(-10, 10, len(params[::5]))
+        want = o.ln_posterior_batch(params)
+        c = Case.__new__(Case)
+        c.wl, c.flux, c.err, c.comps, c.bc, c.bpc = wl, d, e, comps, True, True
+        m = _model(c)
+        got = m.lnposterior_batch(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL
+
+
+def test_bank_equals_direct_broadening():
+    """The exact sigma bank and the per-walker broadening kernel give the same bits."""
+    from spamm_b200 import _lib
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg5_full")
+    a = _model(c, _lib.TEMPLATES_BANK)
+    b = _model(c, _lib.TEMPLATES_DIRECT)
+    assert a.plan.template_mode == _lib.TEMPLATES_BANK and a.plan.bank_rows > 100
+    assert b.plan.template_mode == _lib.TEMPLATES_DIRECT
+    ga, gb = a.lnposterior_batch(c.params), b.lnposterior_batch(c.params)
+    assert np.array_equal(ga, gb)
+    fa, fb = a.model_flux_batch(c.params[:8]), b.model_flux_batch(c.params[:8])
+    assert np.array_equal(fa, fb)
+
+
+def test_flux_outside_prior_uses_direct_kernel():
+    """component.flux() with a width no prior admits (bank miss) still matches the oracle."""
+    from oracle.spamm_numpy import OracleModel
+    from spamm_b200.Spectrum import Spectrum
+    wl = grid(2048)
+    o = OracleModel(wl, wl, wl, comps=["FE"])
+    p = np.array([[1e-14, 2e-14, 3e-14, 14000.0], [1e-14, 2e-14, 3e-14, 2500.0]])
+    want = np.array([o.component_flux("FE", q) for q in p])
+    fe = _components(["FE"])[0]
+    sp = Spectrum(wl, wl, wl)
+    fe.initialize(sp)
+    got = fe.flux_batch(sp, p)
+    assert np.max(np.abs(got - want)) / np.max(np.abs(want)) < FLUX_RTOL
+
+
+def test_model_api_pieces_agree():
+    """prior + likelihood(model_flux) == ln_posterior, through the separate kernels."""
+    z, _ = lnpost_cases()
+    c = Case(z, "full_fp6")
+    m = _model(c)
+    got = m.lnposterior_batch(c.params)
+    for i in (0, 3, len(c.params) - 1):
+        lp = m.prior(c.params[i])
+        assert (lp == 0) == np.isfinite(c.lnpost[i])
+        if lp == 0:
+            f = m.model_flux(c.params[i])
+            v = m.likelihood(f) + lp
+            assert abs(v - got[i]) <= 1e-12 * abs(got[i])
+
+
+def test_full_size_properties():
+    """BASELINE config 5 size (8192 px; walkers reduced only where a [W,P] array is
+    materialised): determinism, batch-independence, permutation equivariance, and
+    exact linearity of the model flux in the normalisations."""
+    import torch
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg5_full")
+    m = _model(c)
+    rng = np.random.RandomState(5)
+    lo, hi = m.plan.lo, m.plan.hi
+    W = 8192
+    params = lo + (hi - lo) * rng.rand(W, len(lo))
+    params[:81] = c.params                           # includes out-of-prior rows
+    a = m.lnposterior_batch(params)
+    b = m.lnposterior_batch(params)
+    assert np.array_equal(a, b)
+    assert rel_err(a[:81], c.lnpost).max() < LNPOST_RTOL
+    perm = rng.permutation(W)
+    assert np.array_equal(m.lnposterior_batch(params[perm]), a[perm])
+    assert np.array_equal(m.lnposterior_batch(params[100:357]), a[100:357])
+    assert np.all(np.isfinite(a[81:])) and np.all(a[81:] < 0)
+    # device-resident entry point gives the same bits as the host-buffer one
+    d = torch.from_numpy(params).cuda()
+    assert np.array_equal(m.plan.lnposterior(d).cpu().numpy(), a)
+    # doubling every normalisation doubles the model flux exactly
+    sub = params[81:81 + 64].copy()
+    f1 = m.model_flux_batch(sub)
+    norm_idx = [0, 2, 3, 4, 6, 7, 8, 9, 10, 11, 12, 14]
+    sub2 = sub.copy()
+    sub2[:, norm_idx] *= 2.0
+    f2 = m.model_flux_batch(sub2)
+    assert np.array_equal(f2, 2.0 * f1)
+    assert m.plan.status() == 0
+
+
+def test_empty_and_ragged_batches():
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg2_nc_fe")
+    m = _model(c)
+    assert m.lnposterior_batch(np.zeros((0, len(c.lo)))).shape == (0,)
+    one = m.lnposterior_batch(c.params[:1])
+    assert rel_err(one, c.lnpost[:1]).max() < LNPOST_RTOL
+    with pytest.raises(ValueError):
+        m.lnposterior_batch(np.zeros((3, len(c.lo) + 1)))
+    # more walkers than the plan's staging capacity: chunked inside the library
+    m2 = _model(c)
+    m2.max_walkers = 16
+    big = np.tile(c.params, (3, 1))
+    assert np.array_equal(m2.lnposterior_batch(big), np.tile(m.lnposterior_batch(c.params), 3))
