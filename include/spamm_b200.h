@@ -104,6 +104,9 @@ typedef struct SpammPlanDesc {
     int32_t balmer_line_type;                  /* SpammLineType, bc_line_type   */
     int32_t balmer_line_min;                   /* int(bc_lines_min) = 3         */
     int32_t balmer_n_lines;                    /* len(np.arange(bc_lines_min, bc_lines_max)) = 397 */
+    int32_t balmer_exact_line_sum;             /* 0: far-field cluster series for distant line groups
+                                                  (<= 1e-15 relative, default); 1: every line summed
+                                                  directly like makelines (BC:315-333) */
     const double* balmer_line_center;          /* [n_lines] balmerseries(), :247-259 */
     const double* balmer_line_exparg;          /* [n_lines] E0*(1/n^2 - 1/(n-1)^2), :296 */
     double sh95_ne[SPAMM_SH95_NE];             /* knots of the 48 pickled interp2d objects, :288-290 */

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libspamm_b200.so")
+LIB_PATH = os.environ.get("SPAMM_B200_LIB", os.path.join(PKG, "libspamm_b200.so"))
 
 ABI_VERSION = 1
 MAX_COMPONENTS = 8
@@ -60,6 +60,7 @@ class SpammPlanDesc(ctypes.Structure):
         ("balmer_line_type", ctypes.c_int32),
         ("balmer_line_min", ctypes.c_int32),
         ("balmer_n_lines", ctypes.c_int32),
+        ("balmer_exact_line_sum", ctypes.c_int32),
         ("balmer_line_center", c_double_p),
         ("balmer_line_exparg", c_double_p),
         ("sh95_ne", ctypes.c_double * SH95_NE),

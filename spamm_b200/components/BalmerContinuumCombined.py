@@ -37,6 +37,9 @@ class BalmerCombined(Component):
         self.logNe_max = self.inputpars["bc_logNe_max"]
         self.BC = BalmerContinuum
         self.BpC = BalmerPseudocContinuum
+        # GPU line-sum strategy: False = far-field series for distant line clusters (default,
+        # <= 1e-15 relative), True = every one of the 397 lines summed directly (BC:315-333)
+        self.exact_line_sum = bool(self.inputpars.get("bc_exact_line_sum", False))
 
     @property
     def is_analytic(self):
@@ -91,6 +94,7 @@ class BalmerCombined(Component):
         minline = int(line_orders.min())
         desc.balmer_line_min = minline
         desc.balmer_n_lines = len(line_orders)
+        desc.balmer_exact_line_sum = 1 if self.exact_line_sum else 0
         centers, cp = _lib.as_c(self.balmerseries(line_orders))
         # E0*(1./i**2-1./(i-1)**2) for integer i (BC:296)
         ns = [minline + k for k in range(len(line_orders))]

@@ -46,7 +46,10 @@ static int set_error(int code, const std::string& msg) {
 // device-side plan
 // ---------------------------------------------------------------------------
 constexpr int kThreads = 256;          // threads per CTA of the fused kernel
-constexpr int kPix = 2;                // pixels per thread in the line loop
+#ifndef SPAMM_PIX
+#define SPAMM_PIX 2
+#endif
+constexpr int kPix = SPAMM_PIX;        // pixels per lane in the line loop
 constexpr int kMaxDim = 64;            // max parameters per walker
 constexpr int kMaxLines = 1024;
 constexpr int kConvTile = 256;
@@ -55,6 +58,13 @@ enum StatusBits : int {
     kStatSigmaRange = 1,   // sigma_norm outside the bank / < 1
     kStatBcKernel = 2,     // log_conv kernel wider than one pixel (unsupported)
     kStatBcStage = 4,      // BC edge pixel beyond the staged f0 range
+};
+
+constexpr int kMaxClusters = 6;
+constexpr int kMom = 16;               // series terms kept (validated: <= 1e-15 at rho <= 0.1)
+struct ClusterDev {
+    int g_lo, g_hi;                    // line groups (of 4) covered
+    double cb0, R0;                    // centre and half-span at zero velocity offset
 };
 
 struct TemplDev {
@@ -85,7 +95,9 @@ struct PlanDev {
     int comp_off[SPAMM_MAX_COMPONENTS];
     // NC
     int nc_broken;
-    const double* nc_x;                   // wl / norm_wl
+    const double *nc_lnx_hi, *nc_lnx_lo;  // ln(wl / norm_wl) as a double-double
+    const double* inv_err;                // 1 / flux_error
+    int n_chunks;                         // ceil(P / 64): warp tasks of the fused kernel
     // templates
     TemplDev fe, host;
     // Balmer
@@ -93,8 +105,16 @@ struct PlanDev {
     const double *line_c0, *line_e;
     double sh_ne[SPAMM_SH95_NE], sh_T[SPAMM_SH95_T];
     const double* sh_z;
-    const double *bc_hnu, *bc_b1, *bc_lam2, *bc_t3, *bc_lnnew, *bc_expnew;
-    const int *bc_jA, *bc_kB;
+    // far-field clusters of the line forest (see DESIGN.md "line-sum"): contiguous groups of
+    // lines whose sum is evaluated as a truncated Taylor series in (c_n - c_bar)/R when the
+    // pixel is >= 10 R away in the complex plane; cl[n_clusters] is the union ("super") cluster
+    int series_on, n_clusters, has_super, g_direct_end;
+    ClusterDev cl[kMaxClusters + 1];
+    const double *line_d, *line_dS;       // scaled offsets within the base / super cluster
+    const double *bc_hnu, *bc_K, *bc_t3;
+    const int4* bc_idx;                   // 4 source pixels of the log_conv stencil
+    const double *bc_tb0, *bc_tb1, *bc_ta;
+    int edge_guess;                       // insertion point of balmer_edge in wl
     int bc_nstage;
     double bc_dlnew;
     double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
@@ -165,32 +185,19 @@ __device__ int nearest_index(const double* __restrict__ wl, int n, double v) {
     return c;
 }
 
-// reciprocal to ~1 ulp: MUFU.RCP64H seed + two Newton steps (4 DFMA), no
-// special-case slow path (arguments here are products of (dl^2 + w^2) terms,
-// always normal and positive)
+// reciprocal to <= 1 ulp: MUFU.RCP64H seed (measured 2^-20 on B200, tools/rcp_probe.cu)
+// + one cubic Newton step y(1 + e + e^2), e = 1 - x y  (3 DFMA), no special-case slow path
+// (arguments here are products of (dl^2 + w^2) terms, always normal and positive)
 __device__ __forceinline__ double rcp_fast(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    return y;
+    return fma(y, fma(e, e, e), y);
 }
 
 // ---------------------------------------------------------------------------
 // setup kernels (plan creation)
 // ---------------------------------------------------------------------------
-// log_conv resampling operator (BC:218-241): bins of the two np.interp calls
-__global__ void k_bc_bins(int P, const double* __restrict__ wl, const double* __restrict__ lnwl,
-                          const double* __restrict__ lnnew, const double* __restrict__ expnew,
-                          int* __restrict__ jA, int* __restrict__ kB) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    jA[i] = np_bin(expnew, P, wl[i]);      // np.interp(wavelength, exp(ln_wavenew), flux_conv)
-    kB[i] = np_bin(lnwl, P, lnnew[i]);     // np.interp(ln_wavenew, ln_wave, orig_flux)
-}
-
 // Gaussian broadening in ln-lambda space for a list of rows (template t, sigma_norm):
 //   kernel = signal.gaussian(K*sigma, sigma)/(sqrt(2 pi) sigma)          Fe:291-293 / HG:298-300
 //   conv   = np.convolve(log_flux, kernel, mode="same")                  Fe:304     / HG:311
@@ -327,113 +334,194 @@ __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) 
     return ((1 - tx) * (1 - ty) * z00 + tx * (1 - ty) * z10 + (1 - tx) * ty * z01) + tx * ty * z11;
 }
 
-// unnormalised Balmer continuum sample: (1 - exp(-tau)) * blackbody_lambda     BC:435-440
+// unnormalised Balmer continuum sample (1 - exp(-tau)) * blackbody_lambda (BC:435-440).
+// bc_K[k] = 2 h nu^3 c_AA / (c_cgs^2 lambda^2) is the walker-independent factor of B_lambda.
 __device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double tauBE) {
     double log_boltz = pl.bc_hnu[k] / kT;
     double boltzm1 = expm1(log_boltz);
-    double bnu = pl.bc_b1[k] / (pl.c_cgs2 * boltzm1);
-    double flam = bnu * pl.c_aa / pl.bc_lam2[k];
+    double flam = pl.bc_K[k] / boltzm1;
     double tau = tauBE * pl.bc_t3[k];
     double absorption = 1 - exp(-tau);
     return absorption * flam;
 }
 
-// flux_rebin[j] = np.interp(ln_wavenew[j], ln_wave, f0)                         BC:225
-__device__ __forceinline__ double bc_fr(const PlanDev& pl, const double* __restrict__ f0s, int j) {
-    int k = pl.bc_kB[j];
-    if (k < 0) return f0s[0];
-    if (k >= pl.P - 1) return f0s[pl.P - 1];
-    double x = pl.bc_lnnew[j];
-    double x0 = pl.lnwl[k];
-    if (x0 == x) return f0s[k];
-    return np_lerp(x, x0, pl.lnwl[k + 1], f0s[k], f0s[k + 1]);
-}
-
-// log_conv output at data pixel i (kernel == [1.0], see k_lnpost prologue)     BC:239
+// log_conv output at data pixel i (BC:225-239 with kernel == [1.0]): the two np.interp
+// resamplings collapse to a 4-tap stencil on f0 with walker-independent weights
+//   fr_j = f0[k] + (f0[k+1]-f0[k]) tB_j ;  out_i = fr_j + (fr_{j+1}-fr_j) tA_i
 __device__ __forceinline__ double bc_conv_at(const PlanDev& pl, const double* __restrict__ f0s, int i) {
-    int j = pl.bc_jA[i];
-    if (j < 0) return bc_fr(pl, f0s, 0);
-    if (j >= pl.P - 1) return bc_fr(pl, f0s, pl.P - 1);
-    double x = pl.wl[i];
-    double x0 = pl.bc_expnew[j];
-    if (x0 == x) return bc_fr(pl, f0s, j);
-    return np_lerp(x, x0, pl.bc_expnew[j + 1], bc_fr(pl, f0s, j), bc_fr(pl, f0s, j + 1));
+    const int4 kk = pl.bc_idx[i];              // k0, k0', k1, k1'
+    const double tb0 = pl.bc_tb0[i], tb1 = pl.bc_tb1[i], ta = pl.bc_ta[i];
+    double a0 = f0s[kk.x], a1 = f0s[kk.z];
+    double fr0 = a0 + (f0s[kk.y] - a0) * tb0;
+    double fr1 = a1 + (f0s[kk.w] - a1) * tb1;
+    return fr0 + (fr1 - fr0) * ta;
 }
 
-// highest f0 index bc_conv_at(i) touches
-__device__ __forceinline__ int bc_max_src(const PlanDev& pl, int i) {
-    int j = pl.bc_jA[i];
-    j = j < 0 ? 0 : (j >= pl.P - 1 ? pl.P - 1 : j + 1);
-    int k = pl.bc_kB[j];
-    k = k < 0 ? 0 : (k >= pl.P - 1 ? pl.P - 1 : k + 1);
-    return k;
-}
+struct alignas(16) ClusterW {    // per-walker constants of one cluster
+    double cb, kcb2, twoR, twoRkcb, negAs, thr, As, pad;
+    double mom[kMom];
+};
 
 struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     double p[kMaxDim];
+    ClusterW cw[kMaxClusters + 1];
     TemplCoef fe[SPAMM_MAX_TEMPLATES];
     TemplCoef host[SPAMM_MAX_TEMPLATES];
     double red[kThreads / 32];
     double nc_norm, nc_slope1, nc_slope2, nc_break;
-    double bc_scale, bpc_scale;      // normalization / fnorm
+    double bc_scale;                 // normalization / fnorm
     double kT, tauBE;
     int bc_istar, bpc_istar;
     int prior_ok;
+    int next_task;
 };
-
 static_assert(sizeof(WalkerCtx) % 16 == 0, "line table must stay 16-byte aligned");
 
-// cheap components of pixel i: NC + Fe + host, in Model.model_flux order (Model.py:353-364)
-__device__ __forceinline__ double cheap_flux(const PlanDev& pl, const WalkerCtx& c, uint32_t mask,
-                                             int i, double balmer, bool have_balmer) {
-    double m = 0.0;
-    for (int q = 0; q < pl.n_comp; ++q) {
-        if (!((mask >> q) & 1u)) continue;
-        int kind = pl.comp_kind[q];
-        if (kind == SPAMM_COMP_NUCLEAR) {
-            double v;
-            if (!pl.nc_broken) {
-                v = c.nc_norm * pow(pl.nc_x[i], -c.nc_slope1);                    // NC:195
-            } else {
-                double lam = pl.wl[i];
-                double alpha = lam < c.nc_break ? c.nc_slope1 : c.nc_slope2;      // NC:199
-                v = c.nc_norm * pow(lam / c.nc_break, -alpha);
-            }
-            m = m + v;
-        } else if (kind == SPAMM_COMP_FE) {
-            double s = 0.0;
-            for (int t = 0; t < pl.fe.n_templ; ++t) s = s + c.fe[t].a * c.fe[t].f[i];    // Fe:334
-            m = m + s;
-        } else if (kind == SPAMM_COMP_HOST) {
-            double s = 0.0;
-            for (int t = 0; t < pl.host.n_templ; ++t) s = s + c.host[t].a * c.host[t].f[i];  // HG:339
-            m = m + s;
-        } else if (kind == SPAMM_COMP_BALMER) {
-            if (have_balmer) m = m + balmer;
-        }
-    }
-    return m;
+// utils/find_nearest_index.py:33 starting from the plan-time insertion point of the
+// Balmer edge (the per-walker edge moves by < 0.2 A, i.e. a pixel or two)
+__device__ int nearest_index_guess(const double* __restrict__ wl, int n, double v, int g) {
+    if (isnan(v)) return 0;
+    int lo = min(max(g, 0), n);                  // want: first index with wl[lo] >= v
+    int steps = 0;
+    while (lo > 0 && wl[lo - 1] >= v && steps < 32) { --lo; ++steps; }
+    while (lo < n && wl[lo] < v && steps < 32) { ++lo; ++steps; }
+    if (steps >= 32) return nearest_index(wl, n, v);
+    int c = lo;
+    if (c >= n) c = n - 1;
+    if (c > 0 && fabs(wl[c - 1] - v) <= fabs(wl[c] - v)) c = c - 1;
+    while (c > 0 && fabs(wl[c - 1] - v) == fabs(wl[c] - v)) --c;
+    return c;
 }
 
+// one non-Balmer component at pixel i (Model.model_flux adds components in list order)
+__device__ __forceinline__ double comp_flux(const PlanDev& pl, const WalkerCtx& c, int kind, int i) {
+    if (kind == SPAMM_COMP_NUCLEAR) {
+        if (!pl.nc_broken) {
+            // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x held in
+            // double-double, so the result is within ~1 ulp of pow()
+            double s = -c.nc_slope1, hi = pl.nc_lnx_hi[i];
+            double th = s * hi;
+            double tl = fma(s, hi, -th) + s * pl.nc_lnx_lo[i];
+            double v = exp(th);
+            v = fma(v, tl, v);
+            return c.nc_norm * v;
+        }
+        double lam = pl.wl[i];
+        double alpha = lam < c.nc_break ? c.nc_slope1 : c.nc_slope2;              // NC:199
+        return c.nc_norm * pow(lam / c.nc_break, -alpha);
+    }
+    if (kind == SPAMM_COMP_FE) {
+        double s = 0.0;
+        for (int t = 0; t < pl.fe.n_templ; ++t) s = s + c.fe[t].a * c.fe[t].f[i];        // Fe:334
+        return s;
+    }
+    double s = 0.0;                                                                       // host
+    for (int t = 0; t < pl.host.n_templ; ++t) s = s + c.host[t].a * c.host[t].f[i];      // HG:339
+    return s;
+}
+
+// sum of Lorentzians a/(d^2+w^2) over line groups [g0, g1): four lines share one reciprocal
+__device__ __forceinline__ void lorentz_direct(const double2* __restrict__ sL2, int g0, int g1,
+                                               const double (&lam)[kPix], double (&acc)[kPix]) {
+#pragma unroll 1
+    for (int g = g0; g < g1; ++g) {
+        const double2 c01 = sL2[g * 6 + 0], c23 = sL2[g * 6 + 1];
+        const double2 w01 = sL2[g * 6 + 2], w23 = sL2[g * 6 + 3];
+        const double2 a01 = sL2[g * 6 + 4], a23 = sL2[g * 6 + 5];
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+            double d0 = lam[q] - c01.x, d1 = lam[q] - c01.y;
+            double d2 = lam[q] - c23.x, d3 = lam[q] - c23.y;
+            double x0 = fma(d0, d0, w01.x), x1 = fma(d1, d1, w01.y);
+            double x2 = fma(d2, d2, w23.x), x3 = fma(d3, d3, w23.y);
+            double p01 = x0 * x1, p23 = x2 * x3;
+            double n01 = fma(a01.x, x1, a01.y * x0);
+            double n23 = fma(a23.x, x3, a23.y * x2);
+            double num = fma(n01, p23, n23 * p01);
+            double den = p01 * p23;
+            acc[q] = fma(num, rcp_fast(den), acc[q]);
+        }
+    }
+}
+
+// min over the warp's pixels of C = u^2 + kappa c_bar^2 (squared distance to the cluster's
+// pole line, up to the factor 1/(1+kappa)); warp-uniform result
+__device__ __forceinline__ double cluster_cmin(const ClusterW& cw, const double (&lam)[kPix]) {
+    double cmin = CUDART_INF;
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+        double u = lam[q] - cw.cb;
+        cmin = fmin(cmin, fma(u, u, cw.kcb2));
+    }
+    for (int o = 16; o > 0; o >>= 1) cmin = fmin(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+    return cmin;
+}
+
+// sum_n a_n / q_n(lam) for one cluster as sum_k t_k M_k:
+//   1/q(delta) = sum_k t_k (delta/R)^k,  t_0 = 1/C, t_1 = beta t_0, t_k = beta t_{k-1} + alpha t_{k-2}
+//   with q(delta) = As (delta/R)^2 - 2R(u - kappa c_bar)(delta/R) + C
+__device__ __forceinline__ void cluster_series(const ClusterW& cw, int K, const double (&lam)[kPix],
+                                               double (&acc)[kPix]) {
+    double t1[kPix], t2[kPix], al[kPix], be[kPix], sum[kPix];
+    const double m0 = cw.mom[0], m1 = cw.mom[1];
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) {
+        double u = lam[q] - cw.cb;
+        double invC = rcp_fast(fma(u, u, cw.kcb2));
+        be[q] = fma(u, cw.twoR, -cw.twoRkcb) * invC;
+        al[q] = cw.negAs * invC;
+        t2[q] = invC;
+        t1[q] = be[q] * invC;
+        sum[q] = fma(t1[q], m1, invC * m0);
+    }
+#pragma unroll 1
+    for (int k = 2; k < K; ++k) {
+        const double mk = cw.mom[k];
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+            double t = fma(be[q], t1[q], al[q] * t2[q]);
+            sum[q] = fma(t, mk, sum[q]);
+            t2[q] = t1[q];
+            t1[q] = t;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) acc[q] += sum[q];
+}
+
+// number of series terms for rho^2 = As / Cmin  (rho^K <~ 1e-16; capped at kMom, which the
+// far test rho <= 0.1 makes sufficient)
+__device__ __forceinline__ int series_terms(double rho2) {
+    float l = -__logf((float)rho2);
+    int K = (int)(74.0f / l) + 1;
+    return min(max(K, 3), kMom);
+}
+
+#ifndef SPAMM_MIN_BLOCKS
+#define SPAMM_MIN_BLOCKS 3
+#endif
+constexpr int kChunk = 32 * kPix;      // pixels per warp task
+
 template <int MODE>   // 0: ln-posterior; 1: model flux out
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
           uint32_t mask, DirectRows dr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WalkerCtx& c = *reinterpret_cast<WalkerCtx*>(smem_raw);
-    double* sLine = reinterpret_cast<double*>(smem_raw + sizeof(WalkerCtx));   // [3][n_lines_pad] grouped
+    double* sLine = reinterpret_cast<double*>(smem_raw + sizeof(WalkerCtx));   // [n_pad/4][12] grouped
     double* sG = sLine + 3 * pl.n_lines_pad;                                    // [n_lines_pad]
     double* sW = sG + pl.n_lines_pad;                                           // [n_lines_pad]
-    double* sF0 = sW + pl.n_lines_pad;                                          // [bc_nstage]
+    double* sChi = sW + pl.n_lines_pad;                                         // [n_chunks]
+    double* sF0 = sChi + pl.n_chunks;                                           // [bc_nstage]
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wloc = blockIdx.x;           // walker within this launch
     const int w = w0 + wloc;
     const int P = pl.P;
     const double* pw = params + (size_t)w * pl.D;
 
-    // ---- parameters + flat-box prior (Model.prior, Model.py:449-470) -----------
-    if (tid == 0) c.prior_ok = 1;
+    // ---- P0: parameters + flat-box prior (Model.prior, Model.py:449-470) -----------------
+    if (tid == 0) { c.prior_ok = 1; c.next_task = 0; }
     __syncthreads();
     if (tid < pl.D) {
         double v = pw[tid];
@@ -448,8 +536,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         return;
     }
 
-    // ---- which components are live ----------------------------------------------
-    int off_nc = -1, off_bal = -1;
+    // ---- which components are live ------------------------------------------------------
+    int off_nc = -1, off_bal = -1, q_bal = pl.n_comp;
     bool has_fe = false, has_host = false;
     for (int q = 0; q < pl.n_comp; ++q) {
         if (!((mask >> q) & 1u)) continue;
@@ -457,12 +545,21 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (kind == SPAMM_COMP_NUCLEAR) off_nc = pl.comp_off[q];
         else if (kind == SPAMM_COMP_FE) has_fe = true;
         else if (kind == SPAMM_COMP_HOST) has_host = true;
-        else if (kind == SPAMM_COMP_BALMER) off_bal = pl.comp_off[q];
+        else if (kind == SPAMM_COMP_BALMER) { off_bal = pl.comp_off[q]; q_bal = q; }
     }
-    const bool do_bc = off_bal >= 0 && pl.bc_on;
-    const bool do_bpc = off_bal >= 0 && pl.bpc_on;
+    const bool have_balmer = off_bal >= 0;
+    const bool do_bc = have_balmer && pl.bc_on;
+    const bool do_bpc = have_balmer && pl.bpc_on;
 
-    // ---- per-walker scalars --------------------------------------------------------
+    double b_norm = 0, b_Te = 0, b_tau = 0, b_loff = 0, b_lwid = 0, b_logNe = 0;
+    if (have_balmer) {
+        b_norm = c.p[off_bal]; b_Te = c.p[off_bal + 1]; b_tau = c.p[off_bal + 2];
+        b_loff = c.p[off_bal + 3]; b_lwid = c.p[off_bal + 4]; b_logNe = c.p[off_bal + 5];
+    }
+    const int n_lines = pl.n_lines, n_pad = pl.n_lines_pad;
+    const double kT = pl.kb * b_Te;                      // k.value*T, BC:296
+
+    // ---- P1: independent per-walker scalars, spread over the warps ------------------------
     if (tid == 0 && off_nc >= 0) {
         if (!pl.nc_broken) {
             c.nc_norm = c.p[off_nc]; c.nc_slope1 = c.p[off_nc + 1];
@@ -472,10 +569,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             c.nc_slope1 = c.p[off_nc + 2]; c.nc_slope2 = c.p[off_nc + 3];
         }
     }
-    // template rows + coefficients: thread t of warp 1 (Fe) / warp 2 (host)
-    if (has_fe && tid >= 32 && tid < 32 + pl.fe.n_templ) {
+    if (has_fe && warp == 1 && lane < pl.fe.n_templ) {
         const TemplDev& ts = pl.fe;
-        int t = tid - 32;
+        int t = lane;
         double norm = c.p[ts.param_off + t];
         const double* f; double nf;
         if (dr.fe_f != nullptr) {
@@ -492,9 +588,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         c.fe[t].f = f;
         c.fe[t].a = norm / nf;                                          // Fe:334
     }
-    if (has_host && tid >= 64 && tid < 64 + pl.host.n_templ) {
+    if (has_host && warp == 2 && lane < pl.host.n_templ) {
         const TemplDev& ts = pl.host;
-        int t = tid - 64;
+        int t = lane;
         double norm = c.p[ts.param_off + t];
         const double* f; double nf;
         if (dr.host_f != nullptr) {
@@ -511,19 +607,31 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         c.host[t].f = f;
         c.host[t].a = norm / nf;                                        // HG:339
     }
-
-    // ---- Balmer prologue ---------------------------------------------------------------
-    double b_norm = 0, b_Te = 0, b_tau = 0, b_loff = 0, b_lwid = 0, b_logNe = 0;
-    if (off_bal >= 0) {
-        b_norm = c.p[off_bal]; b_Te = c.p[off_bal + 1]; b_tau = c.p[off_bal + 2];
-        b_loff = c.p[off_bal + 3]; b_lwid = c.p[off_bal + 4]; b_logNe = c.p[off_bal + 5];
+    if (warp == 3 && lane == 0) {
+        c.bc_istar = -1;
+        c.kT = kT; c.tauBE = b_tau;
+        if (do_bc) {
+            double edge_wl = pl.edge * (1 - b_loff / pl.c_cgs);          // BC:432 (cm/s!)
+            int is = nearest_index_guess(pl.wl, P, edge_wl, pl.edge_guess);   // BC:443
+            c.bc_istar = is;
+            // log_conv kernel: kernel_width = round(5*dpix) must be 0          BC:229-233
+            double dpix = (b_lwid / pl.c_cgs) / pl.bc_dlnew;
+            if (rint(5 * dpix) != 0.0) atomicOr(pl.status, kStatBcKernel);
+            const int4 kk = pl.bc_idx[is];
+            if (max(kk.y, kk.w) >= pl.bc_nstage) atomicOr(pl.status, kStatBcStage);
+        }
     }
-    const int n_lines = pl.n_lines, n_pad = pl.n_lines_pad;
+    if (warp == 4 && lane == 0) {
+        c.bpc_istar = -1;
+        if (do_bpc) {
+            double edge_wl = pl.edge * (1 - b_loff / pl.c_kms);          // BC:374
+            c.bpc_istar = nearest_index_guess(pl.wl, P, edge_wl, pl.edge_guess);   // BC:382
+        }
+    }
     if (do_bpc) {
         const double shift = b_loff / pl.c_kms;          // BC:379
         const double width = b_lwid / pl.c_kms;
         const double n_e = pow(10.0, b_logNe);           // BC:376
-        const double kT = pl.kb * b_Te;                  // k.value*T, BC:296
         for (int n = tid; n < n_pad; n += kThreads) {
             double lc = 0.0, wv = 0.0, rg = 0.0;
             if (n < n_lines) {
@@ -538,8 +646,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             sW[n] = wv;
             sG[n] = rg;      // ratio (n <= 50) or the recursion factor (n > 50)
         }
-        __syncthreads();
-        if (tid == 0) {
+    }
+    __syncthreads();
+
+    // ---- P2: the serial ratio recursion (one lane) overlapped with the f0 stage (the rest) ---
+    if (tid == 0) {
+        if (do_bpc) {
             // flux_ratios[i] = flux_ratios[i-1] * exp(...)  sequentially, BC:292-296
             double prev = 0.0;    // flux_ratios[-1] of the zero-initialised array
             for (int n = 0; n < n_lines; ++n) {
@@ -547,7 +659,15 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 else { prev = prev * sG[n]; sG[n] = prev; }
             }
         }
-        __syncthreads();
+    } else if (do_bc && tid >= 32) {
+        const double tauBE = b_tau;
+        int nst = min(pl.bc_nstage, P);
+        for (int k = tid - 32; k < nst; k += kThreads - 32) sF0[k] = bc_f0(pl, k, kT, tauBE);
+    }
+    __syncthreads();
+
+    // ---- P3: finish the line table; BC normaliser ---------------------------------------------
+    if (do_bpc) {
         for (int n = tid; n < n_pad; n += kThreads) {
             int gq = n >> 2, r4 = n & 3;
             double wv = sW[n], rr = sG[n];
@@ -560,40 +680,19 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
         }
     }
-    if (tid == 0) {
-        c.bc_istar = -1; c.bpc_istar = -1; c.bc_scale = 0; c.bpc_scale = 0;
-        c.kT = pl.kb * b_Te; c.tauBE = b_tau;
-        if (do_bc) {
-            double edge_wl = pl.edge * (1 - b_loff / pl.c_cgs);          // BC:432 (cm/s!)
-            c.bc_istar = nearest_index(pl.wl, P, edge_wl);               // BC:443
-            // log_conv kernel: kernel_width = round(5*dpix) must be 0          BC:229-233
-            double dpix = (b_lwid / pl.c_cgs) / pl.bc_dlnew;
-            if (rint(5 * dpix) != 0.0) atomicOr(pl.status, kStatBcKernel);
-            if (bc_max_src(pl, c.bc_istar) >= pl.bc_nstage) atomicOr(pl.status, kStatBcStage);
-        }
-        if (do_bpc) {
-            double edge_wl = pl.edge * (1 - b_loff / pl.c_kms);          // BC:374
-            c.bpc_istar = nearest_index(pl.wl, P, edge_wl);              // BC:382
-        }
+    if (do_bc && warp == 7 && lane == 0) {
+        double fnorm = bc_conv_at(pl, sF0, c.bc_istar);                  // BC:444
+        c.bc_scale = b_norm / fnorm;                                     // BC:446
     }
     __syncthreads();
 
-    // ---- BC: stage f0 and normalise ---------------------------------------------------
-    if (do_bc) {
-        const double kT = c.kT, tauBE = c.tauBE;
-        int nst = min(pl.bc_nstage, P);
-        for (int k = tid; k < nst; k += kThreads) sF0[k] = bc_f0(pl, k, kT, tauBE);
-        __syncthreads();
-        if (tid == 0) {
-            double fnorm = bc_conv_at(pl, sF0, c.bc_istar);              // BC:444
-            c.bc_scale = b_norm / fnorm;                                 // BC:446
-        }
-    }
-    // ---- BpC normaliser: the line sum at the edge pixel (BC:385) -----------------------
-    if (do_bpc && tid < 32) {
-        const double lam = pl.wl[c.bpc_istar];
+    // ---- P4: BpC normaliser = the line sum at the edge pixel (BC:385), all threads ----------------
+    const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
+    double bpc_scale = 0.0;
+    if (do_bpc) {
+        const double lam = pl.wl[bpc_istar];
         double s = 0.0;
-        for (int n = tid; n < n_lines; n += 32) {
+        for (int n = tid; n < n_lines; n += kThreads) {
             int gq = n >> 2, r4 = n & 3;
             double d = lam - sLine[gq * 12 + r4];
             double w2 = sLine[gq * 12 + 4 + r4];
@@ -602,112 +701,147 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             else s += a * exp(-(d * d) / w2);
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (tid == 0) c.bpc_scale = b_norm / s;                          // BC:387
+        if (lane == 0) c.red[warp] = s;
+        // cluster moments M_k = sum_n a_n d_n^k and per-walker cluster constants: one warp each
+        const int n_cl = pl.series_on && pl.line_type == SPAMM_LINE_LORENTZIAN
+                             ? pl.n_clusters + (pl.has_super ? 1 : 0) : 0;
+        if (warp < n_cl) {
+            const ClusterDev& cd = pl.cl[warp];
+            const double* dd = (warp == pl.n_clusters) ? pl.line_dS : pl.line_d;
+            double mk[kMom];
+#pragma unroll
+            for (int k = 0; k < kMom; ++k) mk[k] = 0.0;
+            for (int n = cd.g_lo * 4 + lane; n < cd.g_hi * 4; n += 32) {
+                double pw = sLine[(n >> 2) * 12 + 8 + (n & 3)];      // a_n = r_n w_n
+                const double dn = dd[n];
+#pragma unroll
+                for (int k = 0; k < kMom; ++k) { mk[k] += pw; pw *= dn; }
+            }
+#pragma unroll
+            for (int k = 0; k < kMom; ++k) {
+                double v = mk[k];
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) c.cw[warp].mom[k] = v;
+            }
+            if (lane == 0) {
+                const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
+                const double kappa = width * width;
+                const double cb = cd.cb0 - shift * cd.cb0, R = cd.R0 - shift * cd.R0;
+                ClusterW& cw = c.cw[warp];
+                cw.cb = cb;
+                cw.kcb2 = kappa * cb * cb;
+                cw.twoR = 2.0 * R;
+                cw.twoRkcb = 2.0 * R * kappa * cb;
+                cw.As = (1.0 + kappa) * R * R;
+                cw.negAs = -cw.As;
+                cw.thr = 100.0 * cw.As;                              // rho <= 0.1
+            }
+        }
+        __syncthreads();
+        double tot = 0.0;
+        for (int q = 0; q < kThreads / 32; ++q) tot += c.red[q];
+        bpc_scale = b_norm / tot;                                        // BC:387
     }
-    __syncthreads();
-
-    const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
-    const double bc_scale = c.bc_scale, bpc_scale = c.bpc_scale;
-    const bool have_balmer = off_bal >= 0;
-    double chi = 0.0;
+    const double bc_scale = c.bc_scale;
     double* fout = (MODE == 1) ? out + (size_t)wloc * P : nullptr;
 
-    // ---- loop A: pixels without line work (i <= bpc_istar, or everything if no BpC) -----
-    const int endA = do_bpc ? min(bpc_istar + 1, P) : P;
-    for (int i = tid; i < endA; i += kThreads) {
-        double balmer = 0.0;
-        if (have_balmer) {
-            double bc = 0.0, bpc = 0.0;
-            if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;   // BC:445-446
-            if (do_bpc) bpc = 0.0 * bpc_scale;                                              // BC:386-387
-            balmer = (do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc);                     // BC:462-471
+    // ---- main phase: each warp pulls 64-pixel tasks, reddest (line-heavy) chunks first ------------
+    const int n_chunks = pl.n_chunks;
+    const int n_groups = n_pad >> 2;
+    const double2* sL2 = reinterpret_cast<const double2*>(sLine);
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&c.next_task, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_chunks) break;
+        const int chunk = n_chunks - 1 - t;
+        int idx[kPix];
+        double m[kPix], acc[kPix];
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+            idx[q] = min(chunk * kChunk + q * 32 + lane, P - 1);
+            acc[q] = 0.0;
+            // components listed before the Balmer component (Model.py:353-364 order)
+            double v = 0.0;
+            for (int k = 0; k < q_bal; ++k)
+                if ((mask >> k) & 1u) v = v + comp_flux(pl, c, pl.comp_kind[k], idx[q]);
+            m[q] = v;
         }
-        double m = cheap_flux(pl, c, mask, i, balmer, have_balmer);
+        if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
+            double lam[kPix];
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) lam[q] = pl.wl[idx[q]];
+            if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
+                if (!pl.series_on) {
+                    lorentz_direct(sL2, 0, n_groups, lam, acc);
+                } else {
+                    lorentz_direct(sL2, 0, pl.g_direct_end, lam, acc);
+                    bool done = false;
+                    if (pl.has_super) {
+                        const ClusterW& cw = c.cw[pl.n_clusters];
+                        double cmin = cluster_cmin(cw, lam);
+                        if (cmin >= cw.thr) { cluster_series(cw, series_terms(cw.As / cmin), lam, acc); done = true; }
+                    }
+                    if (!done) {
+                        for (int k = 0; k < pl.n_clusters; ++k) {
+                            const ClusterW& cw = c.cw[k];
+                            double cmin = cluster_cmin(cw, lam);
+                            if (cmin >= cw.thr) cluster_series(cw, series_terms(cw.As / cmin), lam, acc);
+                            else lorentz_direct(sL2, pl.cl[k].g_lo, pl.cl[k].g_hi, lam, acc);
+                        }
+                    }
+                }
+            } else {
+                for (int n = 0; n < n_lines; ++n) {
+                    int gq = n >> 2, r4 = n & 3;
+                    double lc = sLine[gq * 12 + r4], w2 = sLine[gq * 12 + 4 + r4];
+                    double rr = sLine[gq * 12 + 8 + r4];
+#pragma unroll
+                    for (int q = 0; q < kPix; ++q) {
+                        double d = lam[q] - lc;
+                        acc[q] = fma(rr, exp(-(d * d) / w2), acc[q]);                       // BC:319
+                    }
+                }
+            }
+        }
+        double chi = 0.0;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) {
+            const int i = idx[q];
+            double v = m[q];
+            if (have_balmer) {
+                double bc = 0.0, bpc = 0.0;
+                if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;   // BC:445-446
+                if (do_bpc) bpc = ((i > bpc_istar) ? acc[q] : 0.0) * bpc_scale;                // BC:386-387
+                v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
+            }
+            for (int k = q_bal + 1; k < pl.n_comp; ++k)
+                if ((mask >> k) & 1u) v = v + comp_flux(pl, c, pl.comp_kind[k], i);
+            const bool live = chunk * kChunk + q * 32 + lane < P;
+            if (MODE == 0) {
+                double r = (pl.flux[i] - v) * pl.inv_err[i];                                   // Model.py:440
+                if (live) chi += r * r;
+            } else if (live) {
+                fout[i] = v;
+            }
+        }
         if (MODE == 0) {
-            double r = (pl.flux[i] - m) / pl.err[i];                                        // Model.py:440
-            chi += r * r;
-        } else {
-            fout[i] = m;
+            for (int o = 16; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
+            if (lane == 0) sChi[chunk] = chi;
         }
     }
 
-    // ---- loop B: pixels redward of the edge: 397-line sum ---------------------------------
-    if (do_bpc) {
-        const int n_groups = n_pad >> 2;
-        const double2* sL2 = reinterpret_cast<const double2*>(sLine);
-        for (int base = endA; base < P; base += kThreads * kPix) {
-            double lam[kPix], acc[kPix];
-            int idx[kPix];
-#pragma unroll
-            for (int q = 0; q < kPix; ++q) {
-                idx[q] = base + q * kThreads + tid;
-                lam[q] = pl.wl[min(idx[q], P - 1)];
-                acc[q] = 0.0;
-            }
-            if (base + (tid & ~31) < P) {     // warp has at least one live pixel in slot 0
-                if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
-#pragma unroll 1
-                    for (int g = 0; g < n_groups; ++g) {
-                        const double2 c01 = sL2[g * 6 + 0], c23 = sL2[g * 6 + 1];
-                        const double2 w01 = sL2[g * 6 + 2], w23 = sL2[g * 6 + 3];
-                        const double2 a01 = sL2[g * 6 + 4], a23 = sL2[g * 6 + 5];
-#pragma unroll
-                        for (int q = 0; q < kPix; ++q) {
-                            // four Lorentzians a/(d^2+w^2) over one common denominator
-                            double d0 = lam[q] - c01.x, d1 = lam[q] - c01.y;
-                            double d2 = lam[q] - c23.x, d3 = lam[q] - c23.y;
-                            double x0 = fma(d0, d0, w01.x), x1 = fma(d1, d1, w01.y);
-                            double x2 = fma(d2, d2, w23.x), x3 = fma(d3, d3, w23.y);
-                            double p01 = x0 * x1, p23 = x2 * x3;
-                            double n01 = fma(a01.x, x1, a01.y * x0);
-                            double n23 = fma(a23.x, x3, a23.y * x2);
-                            double num = fma(n01, p23, n23 * p01);
-                            double den = p01 * p23;
-                            acc[q] = fma(num, rcp_fast(den), acc[q]);
-                        }
-                    }
-                } else {
-                    for (int n = 0; n < n_lines; ++n) {
-                        int gq = n >> 2, r4 = n & 3;
-                        double lc = sLine[gq * 12 + r4], w2 = sLine[gq * 12 + 4 + r4];
-                        double rr = sLine[gq * 12 + 8 + r4];
-#pragma unroll
-                        for (int q = 0; q < kPix; ++q) {
-                            double d = lam[q] - lc;
-                            acc[q] = fma(rr, exp(-(d * d) / w2), acc[q]);                   // BC:319
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < kPix; ++q) {
-                int i = idx[q];
-                if (i >= P) continue;
-                double bpc = acc[q] * bpc_scale;                                            // BC:387
-                double bc = 0.0;
-                if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;
-                double balmer = do_bc ? bc + bpc : bpc;
-                double m = cheap_flux(pl, c, mask, i, balmer, true);
-                if (MODE == 0) {
-                    double r = (pl.flux[i] - m) / pl.err[i];
-                    chi += r * r;
-                } else {
-                    fout[i] = m;
-                }
-            }
-        }
-    }
-
-    // ---- per-walker reduction + likelihood (Model.py:440-445) ---------------------------------
+    // ---- per-walker reduction in fixed chunk order + likelihood (Model.py:440-445) ----------------
     if (MODE == 0) {
-        for (int o = 16; o > 0; o >>= 1) chi += __shfl_xor_sync(0xffffffffu, chi, o);
-        if ((tid & 31) == 0) c.red[tid >> 5] = chi;
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             double s = 0.0;
-            for (int q = 0; q < kThreads / 32; ++q) s += c.red[q];
-            double ln_l = -0.5 * (s + pl.sum_ln);
-            out[w] = nan_to_num(ln_l) + 0.0;      // + ln_prior (== 0 inside the box)
+            for (int k = lane; k < n_chunks; k += 32) s += sChi[k];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                double ln_l = -0.5 * (s + pl.sum_ln);
+                out[w] = nan_to_num(ln_l) + 0.0;      // + ln_prior (== 0 inside the box)
+            }
         }
     }
 }
@@ -1016,7 +1150,11 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     if (pl->has_data) {
         if ((rc = upload(pl, d->flux, P, &pd.flux))) return rc;
         if ((rc = upload(pl, d->flux_error, P, &pd.err))) return rc;
+        std::vector<double> ie(P);
+        for (int i = 0; i < P; ++i) ie[i] = 1.0 / d->flux_error[i];
+        if ((rc = upload(pl, ie.data(), P, &pd.inv_err))) return rc;
     }
+    pd.n_chunks = (P + kChunk - 1) / kChunk;
     pd.sum_ln = d->sum_ln_2pi_err2;
     if (d->prior_lo && d->prior_hi) {
         if ((rc = upload(pl, d->prior_lo, d->n_dim, &pd.lo))) return rc;
@@ -1043,12 +1181,18 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     }
     if (off != d->n_dim) return set_error(SPAMM_EINVAL, "n_dim does not match the component list");
 
-    // NC: wl / norm_wl   (PowerLaw1D: x / x_0)
+    // NC: ln(wl / norm_wl) in double-double (PowerLaw1D evaluates (x / x_0) ** (-alpha))
     pd.nc_broken = d->nc_broken_pl;
     if (seen[SPAMM_COMP_NUCLEAR]) {
-        std::vector<double> x(P);
-        for (int i = 0; i < P; ++i) x[i] = d->wl[i] / d->nc_norm_wl;
-        if ((rc = upload(pl, x.data(), P, &pd.nc_x))) return rc;
+        std::vector<double> hi(P), lo(P);
+        for (int i = 0; i < P; ++i) {
+            double x = d->wl[i] / d->nc_norm_wl;
+            long double L = logl((long double)x);
+            hi[i] = (double)L;
+            lo[i] = (double)(L - (long double)hi[i]);
+        }
+        if ((rc = upload(pl, hi.data(), P, &pd.nc_lnx_hi))) return rc;
+        if ((rc = upload(pl, lo.data(), P, &pd.nc_lnx_lo))) return rc;
     }
 
     // templates
@@ -1091,6 +1235,44 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
             pd.line_min = d->balmer_line_min;
             pd.n_lines = d->balmer_n_lines;
             pd.n_lines_pad = (pd.n_lines + 3) & ~3;
+            // far-field clusters over line-table indices; boundaries are multiples of 4 lines.
+            // For bc_lines_min = 3: direct n = 3..18 | 19..30 | 31..50 | 51..98 | 99..max, and the
+            // union of the four as the "super" cluster used by pixels far from the whole forest.
+            pd.series_on = (!d->balmer_exact_line_sum && pd.line_type == SPAMM_LINE_LORENTZIAN) ? 1 : 0;
+            pd.n_clusters = 0; pd.has_super = 0; pd.g_direct_end = pd.n_lines_pad / 4;
+            {
+                const int bounds[5] = {16, 28, 48, 96, pd.n_lines_pad};
+                std::vector<double> dl(pd.n_lines_pad, 0.0), dS(pd.n_lines_pad, 0.0);
+                const double* cc = d->balmer_line_center;
+                auto make = [&](int lo, int hi, ClusterDev* out, std::vector<double>& dd) {
+                    int hi_line = std::min(hi, pd.n_lines);            // exclude padding lines
+                    double cmax = cc[lo], cmin = cc[lo];
+                    for (int n = lo; n < hi_line; ++n) { cmax = std::max(cmax, cc[n]); cmin = std::min(cmin, cc[n]); }
+                    out->g_lo = lo / 4; out->g_hi = hi / 4;
+                    out->cb0 = 0.5 * (cmax + cmin);
+                    out->R0 = 0.5 * (cmax - cmin);
+                    for (int n = lo; n < hi_line; ++n) dd[n] = (cc[n] - out->cb0) / out->R0;
+                };
+                if (pd.series_on && pd.n_lines >= 32) {
+                    pd.g_direct_end = bounds[0] / 4;
+                    for (int b = 0; b < 4; ++b) {
+                        int lo = bounds[b], hi = std::min(bounds[b + 1], pd.n_lines_pad);
+                        if (lo >= pd.n_lines) break;
+                        if (std::min(hi, pd.n_lines) - lo < 2) { hi = pd.n_lines_pad; }
+                        make(lo, hi, &pd.cl[pd.n_clusters], dl);
+                        pd.n_clusters++;
+                        if (hi == pd.n_lines_pad) break;
+                    }
+                    if (pd.n_clusters > 1) {
+                        make(bounds[0], pd.n_lines_pad, &pd.cl[pd.n_clusters], dS);
+                        pd.has_super = 1;
+                    }
+                } else {
+                    pd.series_on = 0;
+                }
+                if ((rc = upload(pl, dl.data(), dl.size(), &pd.line_d))) return rc;
+                if ((rc = upload(pl, dS.data(), dS.size(), &pd.line_dS))) return rc;
+            }
             if ((rc = upload(pl, d->balmer_line_center, pd.n_lines, &pd.line_c0))) return rc;
             if ((rc = upload(pl, d->balmer_line_exparg, pd.n_lines, &pd.line_e))) return rc;
             memcpy(pd.sh_ne, d->sh95_ne, sizeof(pd.sh_ne));
@@ -1102,36 +1284,55 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         if (pd.bc_on) {
             if (!d->bc_ln_wl_new || !d->bc_exp_ln_wl_new)
                 return set_error(SPAMM_EINVAL, "missing log_conv grids");
-            // walker-independent pieces of blackbody_lambda / tau, in the host's operation order
-            std::vector<double> hnu(P), b1(P), lam2(P), t3(P);
+            // walker-independent pieces of blackbody_lambda / tau
+            const double c2 = d->c_cgs * d->c_cgs;                        // c.cgs.value ** 2
+            std::vector<double> hnu(P), K(P), t3(P);
             for (int i = 0; i < P; ++i) {
-                volatile double freq = d->c_aa / d->wl[i];               // c / lambda (AA/s / AA)
-                volatile double hn = d->h_cgs * freq;                     // h*freq
-                volatile double f3 = std::pow((double)freq, 3.0);         // freq ** 3
-                volatile double twoh = 2.0 * d->h_cgs;
-                hnu[i] = hn;
-                b1[i] = twoh * f3;                                        // 2 h freq^3
-                lam2[i] = d->wl[i] * d->wl[i];                            // lam ** 2
-                volatile double r = d->wl[i] / d->balmer_edge;
-                t3[i] = std::pow((double)r, 3.0);                         // (wl/balmer_edge)**3
+                double freq = d->c_aa / d->wl[i];                         // c / lambda
+                hnu[i] = d->h_cgs * freq;                                 // h * freq
+                double b1 = (2.0 * d->h_cgs) * std::pow(freq, 3.0);       // 2 h freq^3
+                double lam2 = d->wl[i] * d->wl[i];
+                K[i] = b1 * d->c_aa / (c2 * lam2);                        // B_lambda = K / expm1(h nu / kT)
+                t3[i] = std::pow(d->wl[i] / d->balmer_edge, 3.0);         // (wl/balmer_edge)**3
             }
             if ((rc = upload(pl, hnu.data(), P, &pd.bc_hnu))) return rc;
-            if ((rc = upload(pl, b1.data(), P, &pd.bc_b1))) return rc;
-            if ((rc = upload(pl, lam2.data(), P, &pd.bc_lam2))) return rc;
+            if ((rc = upload(pl, K.data(), P, &pd.bc_K))) return rc;
             if ((rc = upload(pl, t3.data(), P, &pd.bc_t3))) return rc;
-            if ((rc = upload(pl, d->bc_ln_wl_new, P, &pd.bc_lnnew))) return rc;
-            if ((rc = upload(pl, d->bc_exp_ln_wl_new, P, &pd.bc_expnew))) return rc;
             pd.bc_dlnew = d->bc_ln_wl_new[1] - d->bc_ln_wl_new[0];
-            int *jA, *kB;
-            if ((rc = dalloc(pl, P, &jA))) return rc;
-            if ((rc = dalloc(pl, P, &kB))) return rc;
-            k_bc_bins<<<(P + 255) / 256, 256>>>(P, pd.wl, pd.lnwl, pd.bc_lnnew, pd.bc_expnew, jA, kB);
-            pl->launches += 1;
-            CUDA_TRY(cudaGetLastError());
-            std::vector<int> hjA(P), hkB(P);
-            CUDA_TRY(cudaMemcpy(hjA.data(), jA, P * sizeof(int), cudaMemcpyDeviceToHost));
-            CUDA_TRY(cudaMemcpy(hkB.data(), kB, P * sizeof(int), cudaMemcpyDeviceToHost));
-            pd.bc_jA = jA; pd.bc_kB = kB;
+            // log_conv (BC:218-241) = np.interp onto the uniform ln-lambda grid, identity kernel,
+            // np.interp back: per output pixel a 4-tap stencil with walker-independent weights
+            const double* lnnew = d->bc_ln_wl_new;
+            const double* expnew = d->bc_exp_ln_wl_new;
+            auto bin = [](const double* xp, int n, double x) {
+                if (x < xp[0]) return -1;
+                if (x > xp[n - 1]) return n;
+                int lo = 0, hi = n - 1;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (xp[mid] <= x) lo = mid; else hi = mid; }
+                return xp[hi] <= x ? hi : lo;
+            };
+            auto tap = [&](const double* xp, double x, int* k, double* t) {
+                int j = bin(xp, P, x);
+                if (j < 0) { *k = 0; *t = 0.0; }
+                else if (j >= P - 1) { *k = P - 1; *t = 0.0; }
+                else if (xp[j] == x) { *k = j; *t = 0.0; }
+                else { *k = j; *t = (x - xp[j]) / (xp[j + 1] - xp[j]); }
+            };
+            std::vector<int4> idx(P);
+            std::vector<double> tb0(P), tb1(P), ta(P);
+            for (int i = 0; i < P; ++i) {
+                int j0; double tA;
+                tap(expnew, d->wl[i], &j0, &tA);                       // np.interp(wl, exp(ln_wavenew), .)
+                int j1 = std::min(j0 + 1, P - 1);
+                int k0, k1; double t0, t1;
+                tap(d->ln_wl, lnnew[j0], &k0, &t0);                    // np.interp(ln_wavenew, ln_wave, .)
+                tap(d->ln_wl, lnnew[j1], &k1, &t1);
+                idx[i] = make_int4(k0, std::min(k0 + 1, P - 1), k1, std::min(k1 + 1, P - 1));
+                tb0[i] = t0; tb1[i] = t1; ta[i] = tA;
+            }
+            if ((rc = upload(pl, idx.data(), P, &pd.bc_idx))) return rc;
+            if ((rc = upload(pl, tb0.data(), P, &pd.bc_tb0))) return rc;
+            if ((rc = upload(pl, tb1.data(), P, &pd.bc_tb1))) return rc;
+            if ((rc = upload(pl, ta.data(), P, &pd.bc_ta))) return rc;
             // stage f0 up to the furthest source pixel of (nearest pixel to the edge) + 2
             int ibe = 0;
             double best = INFINITY;
@@ -1139,17 +1340,16 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
                 double v = std::fabs(d->wl[i] - d->balmer_edge);
                 if (v < best) { best = v; ibe = i; }
             }
-            int itop = std::min(ibe + 2, P - 1);
-            int j = hjA[itop];
-            j = j < 0 ? 0 : (j >= P - 1 ? P - 1 : j + 1);
-            int k = hkB[j];
-            k = k < 0 ? 0 : (k >= P - 1 ? P - 1 : k + 1);
-            pd.bc_nstage = std::min(P, k + 2);
+            int itop = std::min(ibe + 2, P - 1), top = 0;
+            for (int i = 0; i <= itop; ++i) top = std::max(top, std::max(idx[i].y, idx[i].w));
+            pd.bc_nstage = std::min(P, top + 1);
         }
+        // insertion point of the Balmer edge: start of the per-walker edge-pixel search
+        pd.edge_guess = (int)(std::lower_bound(d->wl, d->wl + P, d->balmer_edge) - d->wl);
     }
 
     // shared memory of the fused kernel
-    pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.bc_nstage) * sizeof(double);
+    pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.n_chunks + pd.bc_nstage) * sizeof(double);
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
     CUDA_TRY(cudaFuncSetAttribute(k_walkers<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));

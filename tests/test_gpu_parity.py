@@ -227,3 +227,43 @@ def test_empty_and_ragged_batches():
     m2.max_walkers = 16
     big = np.tile(c.params, (3, 1))
     assert np.array_equal(m2.lnposterior_batch(big), np.tile(m.lnposterior_batch(c.params), 3))
+
+
+def test_cluster_series_matches_direct_line_sum():
+    """Far-field series for distant line clusters vs. every line summed directly
+    (makelines, BC:315-333): pixel-wise relative agreement at machine precision over the
+    whole prior range of widths/offsets, on the BASELINE grid and on a ragged one."""
+    from spamm_b200.components.BalmerContinuumCombined import BalmerCombined
+    from spamm_b200.Spectrum import Spectrum
+    from spamm_b200.utils.parse_pars import parse_pars
+    rng = np.random.RandomState(17)
+    for wl in (grid(8192), np.sort(3000.0 + 5000.0 * rng.rand(2500))):
+        sp = Spectrum(wl, wl, wl)
+        pe = parse_pars()["balmer_continuum"]
+        pe["bc_exact_line_sum"] = True
+        exact = BalmerCombined(pars=pe, BalmerContinuum=False, BalmerPseudocContinuum=True)
+        fast = BalmerCombined(BalmerContinuum=False, BalmerPseudocContinuum=True)
+        assert exact.exact_line_sum and not fast.exact_line_sum
+        W = 96
+        p = np.column_stack([rng.uniform(1e-15, 7e-14, W), rng.uniform(500, 1e5, W), rng.uniform(0, 2, W),
+                             rng.uniform(-10, 10, W), rng.uniform(100, 1e4, W), rng.uniform(2, 9, W)])
+        p[:8, 4] = [100.0001, 100.5, 150., 250., 400., 9999., 120., 101.]     # narrowest / broadest lines
+        p[:8, 3] = [-9.999, 9.999, 0., -5., 5., 0., 9.9, -9.9]
+        fe = exact.flux_batch(sp, p)
+        ff = fast.flux_batch(sp, p)
+        nz = fe > 0
+        assert np.array_equal(nz, ff > 0)
+        rel = np.abs(ff[nz] - fe[nz]) / fe[nz]
+        assert rel.max() < 2e-14, rel.max()
+
+
+def test_lnposterior_exact_line_sum_mode_agrees():
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg5_full")
+    m = _model(c)
+    m2 = _model(c)
+    m2.components[-1].exact_line_sum = True
+    m2.invalidate_plan()
+    a, b = m.lnposterior_batch(c.params), m2.lnposterior_batch(c.params)
+    assert rel_err(a, b).max() < 1e-12
+    assert rel_err(b, c.lnpost).max() < LNPOST_RTOL
