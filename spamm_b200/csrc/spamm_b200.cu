@@ -365,8 +365,7 @@ struct alignas(16) ClusterW {    // per-walker constants of one cluster
 struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     double p[kMaxDim];
     ClusterW cw[kMaxClusters + 1];
-    TemplCoef fe[SPAMM_MAX_TEMPLATES];
-    TemplCoef host[SPAMM_MAX_TEMPLATES];
+    TemplCoef tc[2 * SPAMM_MAX_TEMPLATES];   // [0, n_fe): Fe rows, [n_fe, n_fe + n_host): host rows
     double red[kThreads / 32];
     double nc_norm, nc_slope1, nc_slope2, nc_break;
     double bc_scale;                 // normalization / fnorm
@@ -393,31 +392,48 @@ __device__ int nearest_index_guess(const double* __restrict__ wl, int n, double 
     return c;
 }
 
-// one non-Balmer component at pixel i (Model.model_flux adds components in list order)
-__device__ __forceinline__ double comp_flux(const PlanDev& pl, const WalkerCtx& c, int kind, int i) {
-    if (kind == SPAMM_COMP_NUCLEAR) {
-        if (!pl.nc_broken) {
-            // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x held in
-            // double-double, so the result is within ~1 ulp of pow()
-            double s = -c.nc_slope1, hi = pl.nc_lnx_hi[i];
-            double th = s * hi;
-            double tl = fma(s, hi, -th) + s * pl.nc_lnx_lo[i];
-            double v = exp(th);
-            v = fma(v, tl, v);
-            return c.nc_norm * v;
+// NuclearContinuumComponent.flux at pixel i (NC:176-201)
+__device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i) {
+    if (!pl.nc_broken) {
+        // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x held in
+        // double-double, so the result is within ~1 ulp of pow()
+        double s = -c.nc_slope1, hi = pl.nc_lnx_hi[i];
+        double th = s * hi;
+        double tl = fma(s, hi, -th) + s * pl.nc_lnx_lo[i];
+        double v = exp(th);
+        v = fma(v, tl, v);
+        return c.nc_norm * v;
+    }
+    double lam = pl.wl[i];
+    double alpha = lam < c.nc_break ? c.nc_slope1 : c.nc_slope2;              // NC:199
+    return c.nc_norm * pow(lam / c.nc_break, -alpha);
+}
+
+// sum_t a_t f_t[i] over template rows [t0, t0+n) for kPix pixels (Fe:334 / HG:339): all row
+// loads of a block of 8 templates x kPix pixels are issued before any is consumed, so one
+// L2 round trip is exposed instead of one per template
+__device__ __forceinline__ void templ_sum(const WalkerCtx& c, int t0, int n, const int (&idx)[kPix],
+                                          double (&out)[kPix]) {
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) out[q] = 0.0;
+    for (int b = 0; b < n; b += 8) {
+        double v[8][kPix];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool on = b + j < n;
+            const double* f = c.tc[t0 + (on ? b + j : 0)].f;
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) v[j][q] = on ? f[idx[q]] : 0.0;
         }
-        double lam = pl.wl[i];
-        double alpha = lam < c.nc_break ? c.nc_slope1 : c.nc_slope2;              // NC:199
-        return c.nc_norm * pow(lam / c.nc_break, -alpha);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (b + j < n) {
+                const double a = c.tc[t0 + b + j].a;
+#pragma unroll
+                for (int q = 0; q < kPix; ++q) out[q] = out[q] + a * v[j][q];
+            }
+        }
     }
-    if (kind == SPAMM_COMP_FE) {
-        double s = 0.0;
-        for (int t = 0; t < pl.fe.n_templ; ++t) s = s + c.fe[t].a * c.fe[t].f[i];        // Fe:334
-        return s;
-    }
-    double s = 0.0;                                                                       // host
-    for (int t = 0; t < pl.host.n_templ; ++t) s = s + c.host[t].a * c.host[t].f[i];      // HG:339
-    return s;
 }
 
 // sum of Lorentzians a/(d^2+w^2) over line groups [g0, g1): four lines share one reciprocal
@@ -548,6 +564,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         else if (kind == SPAMM_COMP_BALMER) { off_bal = pl.comp_off[q]; q_bal = q; }
     }
     const bool have_balmer = off_bal >= 0;
+    const int n_fe = has_fe ? pl.fe.n_templ : 0, n_host = has_host ? pl.host.n_templ : 0;
     const bool do_bc = have_balmer && pl.bc_on;
     const bool do_bpc = have_balmer && pl.bpc_on;
 
@@ -585,8 +602,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             int row = ts.bank_row0[t] + sig - 1;
             f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
         }
-        c.fe[t].f = f;
-        c.fe[t].a = norm / nf;                                          // Fe:334
+        c.tc[t].f = f;
+        c.tc[t].a = norm / nf;                                          // Fe:334
     }
     if (has_host && warp == 2 && lane < pl.host.n_templ) {
         const TemplDev& ts = pl.host;
@@ -604,8 +621,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             int row = ts.bank_row0[t] + sig - 1;
             f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
         }
-        c.host[t].f = f;
-        c.host[t].a = norm / nf;                                        // HG:339
+        c.tc[n_fe + t].f = f;
+        c.tc[n_fe + t].a = norm / nf;                                        // HG:339
     }
     if (warp == 3 && lane == 0) {
         c.bc_istar = -1;
@@ -756,16 +773,34 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (t >= n_chunks) break;
         const int chunk = n_chunks - 1 - t;
         int idx[kPix];
-        double m[kPix], acc[kPix];
+        double m[kPix], post[kPix], acc[kPix];
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
             idx[q] = min(chunk * kChunk + q * 32 + lane, P - 1);
             acc[q] = 0.0;
-            // components listed before the Balmer component (Model.py:353-364 order)
-            double v = 0.0;
-            for (int k = 0; k < q_bal; ++k)
-                if ((mask >> k) & 1u) v = v + comp_flux(pl, c, pl.comp_kind[k], idx[q]);
-            m[q] = v;
+        }
+        {
+            // component values, then summed in Model.components order (Model.py:353-364):
+            // m = everything listed before the Balmer component, post = everything after it
+            double fe_v[kPix], host_v[kPix], nc_v[kPix];
+            if (n_fe) templ_sum(c, 0, n_fe, idx, fe_v);
+            if (n_host) templ_sum(c, n_fe, n_host, idx, host_v);
+#pragma unroll
+            for (int q = 0; q < kPix; ++q) {
+                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, idx[q]) : 0.0;
+                m[q] = 0.0;
+                post[q] = 0.0;
+            }
+            for (int k = 0; k < pl.n_comp; ++k) {
+                if (!((mask >> k) & 1u) || k == q_bal) continue;
+                const int kind = pl.comp_kind[k];
+#pragma unroll
+                for (int q = 0; q < kPix; ++q) {
+                    const double v = kind == SPAMM_COMP_NUCLEAR ? nc_v[q]
+                                     : (kind == SPAMM_COMP_FE ? fe_v[q] : host_v[q]);
+                    if (k < q_bal) m[q] = m[q] + v; else post[q] = post[q] + v;
+                }
+            }
         }
         if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
             double lam[kPix];
@@ -815,8 +850,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 if (do_bpc) bpc = ((i > bpc_istar) ? acc[q] : 0.0) * bpc_scale;                // BC:386-387
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
-            for (int k = q_bal + 1; k < pl.n_comp; ++k)
-                if ((mask >> k) & 1u) v = v + comp_flux(pl, c, pl.comp_kind[k], i);
+            if (q_bal + 1 < pl.n_comp) v = v + post[q];
             const bool live = chunk * kChunk + q * 32 + lane < P;
             if (MODE == 0) {
                 double r = (pl.flux[i] - v) * pl.inv_err[i];                                   // Model.py:440
