@@ -409,30 +409,40 @@ __device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c,
     return c.nc_norm * pow(lam / c.nc_break, -alpha);
 }
 
-// sum_t a_t f_t[i] over template rows [t0, t0+n) for kPix pixels (Fe:334 / HG:339): all row
-// loads of a block of 8 templates x kPix pixels are issued before any is consumed, so one
-// L2 round trip is exposed instead of one per template
-__device__ __forceinline__ void templ_sum(const WalkerCtx& c, int t0, int n, const int (&idx)[kPix],
-                                          double (&out)[kPix]) {
+// sum_t a_t f_t[i] over N template rows starting at tc[t0] for the task's kPix pixels
+// (i0 + 32 q): every row load is issued before any is consumed, so a single L2 round trip is
+// exposed per block; N is a compile-time count so no predicated-off slots are issued
+template <int N>
+__device__ __forceinline__ void templ_sum_n(const TemplCoef* __restrict__ tc, int i0, double (&out)[kPix]) {
+    double v[N][kPix];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double* f = tc[j].f + i0;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) v[j][q] = f[q * 32];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double a = tc[j].a;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) out[q] = out[q] + a * v[j][q];                    // Fe:334 / HG:339
+    }
+}
+
+__device__ __forceinline__ void templ_sum(const WalkerCtx& c, int t0, int n, int i0, double (&out)[kPix]) {
 #pragma unroll
     for (int q = 0; q < kPix; ++q) out[q] = 0.0;
-    for (int b = 0; b < n; b += 8) {
-        double v[8][kPix];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool on = b + j < n;
-            const double* f = c.tc[t0 + (on ? b + j : 0)].f;
-#pragma unroll
-            for (int q = 0; q < kPix; ++q) v[j][q] = on ? f[idx[q]] : 0.0;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (b + j < n) {
-                const double a = c.tc[t0 + b + j].a;
-#pragma unroll
-                for (int q = 0; q < kPix; ++q) out[q] = out[q] + a * v[j][q];
-            }
-        }
+    const TemplCoef* tc = c.tc + t0;
+    while (n >= 8) { templ_sum_n<8>(tc, i0, out); tc += 8; n -= 8; }
+    switch (n) {
+        case 7: templ_sum_n<7>(tc, i0, out); break;
+        case 6: templ_sum_n<6>(tc, i0, out); break;
+        case 5: templ_sum_n<5>(tc, i0, out); break;
+        case 4: templ_sum_n<4>(tc, i0, out); break;
+        case 3: templ_sum_n<3>(tc, i0, out); break;
+        case 2: templ_sum_n<2>(tc, i0, out); break;
+        case 1: templ_sum_n<1>(tc, i0, out); break;
+        default: break;
     }
 }
 
@@ -490,15 +500,16 @@ __device__ __forceinline__ void cluster_series(const ClusterW& cw, int K, const 
         t1[q] = be[q] * invC;
         sum[q] = fma(t1[q], m1, invC * m0);
     }
+    // two terms per trip (K is made even by series_terms): t2 <- t(k), t1 <- t(k+1)
 #pragma unroll 1
-    for (int k = 2; k < K; ++k) {
-        const double mk = cw.mom[k];
+    for (int k = 2; k < K; k += 2) {
+        const double mk = cw.mom[k], mk1 = cw.mom[k + 1];
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
-            double t = fma(be[q], t1[q], al[q] * t2[q]);
-            sum[q] = fma(t, mk, sum[q]);
-            t2[q] = t1[q];
-            t1[q] = t;
+            t2[q] = fma(be[q], t1[q], al[q] * t2[q]);
+            sum[q] = fma(t2[q], mk, sum[q]);
+            t1[q] = fma(be[q], t2[q], al[q] * t1[q]);
+            sum[q] = fma(t1[q], mk1, sum[q]);
         }
     }
 #pragma unroll
@@ -509,8 +520,8 @@ __device__ __forceinline__ void cluster_series(const ClusterW& cw, int K, const 
 // far test rho <= 0.1 makes sufficient)
 __device__ __forceinline__ int series_terms(double rho2) {
     float l = -__logf((float)rho2);
-    int K = (int)(74.0f / l) + 1;
-    return min(max(K, 3), kMom);
+    int K = ((int)(74.0f / l) + 2) & ~1;          // even
+    return min(max(K, 4), kMom);
 }
 
 #ifndef SPAMM_MIN_BLOCKS
@@ -772,22 +783,20 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n_chunks) break;
         const int chunk = n_chunks - 1 - t;
-        int idx[kPix];
+        // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
+        const int i0 = chunk * kChunk + lane;
         double m[kPix], post[kPix], acc[kPix];
 #pragma unroll
-        for (int q = 0; q < kPix; ++q) {
-            idx[q] = min(chunk * kChunk + q * 32 + lane, P - 1);
-            acc[q] = 0.0;
-        }
+        for (int q = 0; q < kPix; ++q) acc[q] = 0.0;
         {
             // component values, then summed in Model.components order (Model.py:353-364):
             // m = everything listed before the Balmer component, post = everything after it
             double fe_v[kPix], host_v[kPix], nc_v[kPix];
-            if (n_fe) templ_sum(c, 0, n_fe, idx, fe_v);
-            if (n_host) templ_sum(c, n_fe, n_host, idx, host_v);
+            if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
+            if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
-                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, idx[q]) : 0.0;
+                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, i0 + 32 * q) : 0.0;
                 m[q] = 0.0;
                 post[q] = 0.0;
             }
@@ -805,7 +814,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
             double lam[kPix];
 #pragma unroll
-            for (int q = 0; q < kPix; ++q) lam[q] = pl.wl[idx[q]];
+            for (int q = 0; q < kPix; ++q) lam[q] = pl.wl[i0 + 32 * q];
             if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
                 if (!pl.series_on) {
                     lorentz_direct(sL2, 0, n_groups, lam, acc);
@@ -842,7 +851,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         double chi = 0.0;
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
-            const int i = idx[q];
+            const int i = i0 + 32 * q;
             double v = m[q];
             if (have_balmer) {
                 double bc = 0.0, bpc = 0.0;
@@ -851,7 +860,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
             if (q_bal + 1 < pl.n_comp) v = v + post[q];
-            const bool live = chunk * kChunk + q * 32 + lane < P;
+            const bool live = i < P;
             if (MODE == 0) {
                 double r = (pl.flux[i] - v) * pl.inv_err[i];                                   // Model.py:440
                 if (live) chi += r * r;
@@ -1015,11 +1024,16 @@ struct SpammPlan {
     int max_sigma_seen = 0;
 };
 
+// Every device array gets kPad zeroed elements of slack: the fused kernel's last warp task
+// reads pixels [P, P + 63] (results discarded) instead of clamping indices.
+constexpr size_t kPad = 64;
+
 template <typename T>
 static int upload(SpammPlan* pl, const T* host, size_t n, const T** dev_out) {
     T* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&d, (n + kPad) * sizeof(T)));
     pl->allocs.push_back(d);
+    CUDA_TRY(cudaMemset(d, 0, (n + kPad) * sizeof(T)));
     if (n) CUDA_TRY(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *dev_out = d;
     return SPAMM_OK;
@@ -1028,8 +1042,9 @@ static int upload(SpammPlan* pl, const T* host, size_t n, const T** dev_out) {
 template <typename T>
 static int dalloc(SpammPlan* pl, size_t n, T** dev_out) {
     T* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&d, (n + kPad) * sizeof(T)));
     pl->allocs.push_back(d);
+    CUDA_TRY(cudaMemset(d, 0, (n + kPad) * sizeof(T)));
     *dev_out = d;
     return SPAMM_OK;
 }
@@ -1427,11 +1442,13 @@ static int ensure_direct_ws(SpammPlan* pl) {
     int ntm = std::max(pd.fe.n_templ, pd.host.n_templ);
     CUDA_TRY(cudaMalloc(&pl->d_conv, (size_t)chunk * ntm * pl->conv_stride * sizeof(double)));
     if (pd.fe.n_templ) {
-        CUDA_TRY(cudaMalloc(&pl->d_fe_f, (size_t)chunk * pd.fe.n_templ * pd.P * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_fe_f, ((size_t)chunk * pd.fe.n_templ * pd.P + kPad) * sizeof(double)));
+        CUDA_TRY(cudaMemset(pl->d_fe_f, 0, ((size_t)chunk * pd.fe.n_templ * pd.P + kPad) * sizeof(double)));
         CUDA_TRY(cudaMalloc(&pl->d_fe_nf, (size_t)chunk * pd.fe.n_templ * sizeof(double)));
     }
     if (pd.host.n_templ) {
-        CUDA_TRY(cudaMalloc(&pl->d_host_f, (size_t)chunk * pd.host.n_templ * pd.P * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&pl->d_host_f, ((size_t)chunk * pd.host.n_templ * pd.P + kPad) * sizeof(double)));
+        CUDA_TRY(cudaMemset(pl->d_host_f, 0, ((size_t)chunk * pd.host.n_templ * pd.P + kPad) * sizeof(double)));
         CUDA_TRY(cudaMalloc(&pl->d_host_nf, (size_t)chunk * pd.host.n_templ * sizeof(double)));
     }
     CUDA_TRY(cudaMalloc(&pl->d_row_t, (size_t)chunk * ntm * sizeof(int)));
