@@ -296,16 +296,53 @@ def run_ours(args):
 
     value = n_local * world * args.steps / (total_ms * 1e-3)
 
+    # the same ensemble with every Balmer line summed directly (bc_exact_line_sum): this kernel
+    # executes the algorithmic flops of SURVEY.md 8(d), so its FP64 fraction is the comparable one
+    exact_ms = None
+    if rank == 0 and not args.no_exact:
+        from spamm_b200.synth import build_model
+        ds = model.data_spectrum
+        m2 = build_model(list(COMPONENTS), np.asarray(ds.spectral_axis), np.asarray(ds.flux),
+                         np.asarray(ds.flux_error), max_walkers=n_local)
+        m2.components[-1].exact_line_sum = True
+        lnp2 = torch.empty_like(lnp)
+        for _ in range(3):
+            m2.plan.lnposterior(params, out=lnp2)
+        torch.cuda.synchronize()
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for e0, e1 in ev2:
+            flush.zero_()
+            e0.record()
+            m2.plan.lnposterior(params, out=lnp2)
+            e1.record()
+        torch.cuda.synchronize()
+        exact_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev2]))
+        a, b = lnp.cpu().numpy(), lnp2.cpu().numpy()
+        exact_rel = float(np.max(np.abs(a - b) / np.abs(b)))
+
     line = None
     if rank == 0:
         wl = np.asarray(model.data_spectrum.spectral_axis)
         flops = algorithmic_flops(wl, FE_RANGES)
         achieved = flops * (n_local * args.steps / (total_ms * 1e-3)) / 1e12    # this GPU's share
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k_walkers_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
-                    "frac": achieved / float(peak.value) if peak.value else None, "traffic": None,
+                    "frac": achieved / float(peak.value) if peak.value else None, "traffic": traffic,
                     "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); "
                                    "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
-                    "algorithmic_flops_per_eval": flops, "kernel": "k_walkers<0>"}
+                    "algorithmic_flops_per_eval": flops, "kernel": "k_walkers<0>",
+                    "note": "achieved = SURVEY 8(d) algorithmic flops x evals/s; the default kernel sums "
+                            "distant Balmer-line clusters by a far-field series and executes ~6x fewer "
+                            "flops than that count, so frac can exceed 1; exact_line_sum below is the "
+                            "kernel that executes them all"}
+        if exact_ms is not None:
+            ach2 = flops * (n_local / (exact_ms * 1e-3)) / 1e12
+            roofline["exact_line_sum"] = {"ms_per_step": exact_ms, "evals_per_s": n_local / (exact_ms * 1e-3),
+                                          "achieved": ach2, "frac": ach2 / float(peak.value),
+                                          "max_rel_diff_vs_default": exact_rel}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -350,6 +387,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=N_WALKERS, help="walkers per GPU (weak) / total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
