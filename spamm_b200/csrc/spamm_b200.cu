@@ -60,7 +60,7 @@ enum StatusBits : int {
     kStatBcStage = 4,      // BC edge pixel beyond the staged f0 range
 };
 
-constexpr int kMaxClusters = 6;
+constexpr int kMaxClusters = 8;        // base clusters + nested supersets
 constexpr int kMom = 16;               // series terms kept (validated: <= 1e-15 at rho <= 0.1)
 struct ClusterDev {
     int g_lo, g_hi;                    // line groups (of 4) covered
@@ -108,9 +108,9 @@ struct PlanDev {
     // far-field clusters of the line forest (see DESIGN.md "line-sum"): contiguous groups of
     // lines whose sum is evaluated as a truncated Taylor series in (c_n - c_bar)/R when the
     // pixel is >= 10 R away in the complex plane; cl[n_clusters] is the union ("super") cluster
-    int series_on, n_clusters, has_super, g_direct_end;
-    ClusterDev cl[kMaxClusters + 1];
-    const double *line_d, *line_dS;       // scaled offsets within the base / super cluster
+    int series_on, n_clusters, n_super, g_direct_end;
+    ClusterDev cl[kMaxClusters];          // [0,n_clusters) base, then n_super nested supersets, widest first
+    const double* line_d[kMaxClusters];   // per cluster: scaled offsets (c_n - c_bar)/R of its lines
     const double *bc_hnu, *bc_K, *bc_t3;
     const int4* bc_idx;                   // 4 source pixels of the log_conv stencil
     const double *bc_tb0, *bc_tb1, *bc_ta;
@@ -183,6 +183,32 @@ __device__ int nearest_index(const double* __restrict__ wl, int n, double v) {
     if (c > 0 && fabs(wl[c - 1] - v) <= fabs(wl[c] - v)) c = c - 1;
     while (c > 0 && fabs(wl[c - 1] - v) == fabs(wl[c] - v)) --c;
     return c;
+}
+
+// exp(x) for |x| < 700: k = rint(x log2 e) by the magic-number trick, r = x - k ln2 in two FMA
+// steps, degree-11 minimax polynomial (coefficients in constant memory so each DFMA reads its
+// coefficient as a constant-bank operand instead of materialising a 64-bit immediate), scaling by
+// 2^k through the exponent field.  ~25 instructions; agrees with exp() to 1 ulp.  Outside the
+// range (never on the ln-posterior path) the library exp() keeps its overflow/underflow semantics.
+__constant__ double kExpPoly[10] = {
+    2.502232253650299e-08, 2.763090348817311e-07, 2.755751454588244e-06, 2.4801491039099165e-05,
+    0.00019841269589115497, 0.001388888894591638, 0.008333333333455043, 0.041666666666519754,
+    0.16666666666666477, 0.5000000000000012};
+
+__device__ __forceinline__ double exp_fast(double x) {
+    if (!(fabs(x) < 700.0)) return exp(x);
+    const double magic = 6755399441055744.0;
+    double t = fma(x, 1.4426950408889634, magic);
+    int ki = __double2loint(t);
+    double k = t - magic;
+    double r = fma(k, -0.6931471805599453, x);
+    r = fma(k, -2.3190468138462996e-17, r);
+    double p = kExpPoly[0];
+#pragma unroll
+    for (int j = 1; j < 10; ++j) p = fma(p, r, kExpPoly[j]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (ki << 20), __double2loint(p));
 }
 
 // reciprocal to <= 1 ulp: MUFU.RCP64H seed (measured 2^-20 on B200, tools/rcp_probe.cu)
@@ -341,7 +367,7 @@ __device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, dou
     double boltzm1 = expm1(log_boltz);
     double flam = pl.bc_K[k] / boltzm1;
     double tau = tauBE * pl.bc_t3[k];
-    double absorption = 1 - exp(-tau);
+    double absorption = 1 - exp_fast(-tau);
     return absorption * flam;
 }
 
@@ -364,7 +390,7 @@ struct alignas(16) ClusterW {    // per-walker constants of one cluster
 
 struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     double p[kMaxDim];
-    ClusterW cw[kMaxClusters + 1];
+    ClusterW cw[kMaxClusters];
     TemplCoef tc[2 * SPAMM_MAX_TEMPLATES];   // [0, n_fe): Fe rows, [n_fe, n_fe + n_host): host rows
     double red[kThreads / 32];
     double nc_norm, nc_slope1, nc_slope2, nc_break;
@@ -400,7 +426,7 @@ __device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c,
         double s = -c.nc_slope1, hi = pl.nc_lnx_hi[i];
         double th = s * hi;
         double tl = fma(s, hi, -th) + s * pl.nc_lnx_lo[i];
-        double v = exp(th);
+        double v = exp_fast(th);
         v = fma(v, tl, v);
         return c.nc_norm * v;
     }
@@ -525,7 +551,7 @@ __device__ __forceinline__ int series_terms(double rho2) {
 }
 
 #ifndef SPAMM_MIN_BLOCKS
-#define SPAMM_MIN_BLOCKS 3
+#define SPAMM_MIN_BLOCKS 4
 #endif
 constexpr int kChunk = 32 * kPix;      // pixels per warp task
 
@@ -732,10 +758,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (lane == 0) c.red[warp] = s;
         // cluster moments M_k = sum_n a_n d_n^k and per-walker cluster constants: one warp each
         const int n_cl = pl.series_on && pl.line_type == SPAMM_LINE_LORENTZIAN
-                             ? pl.n_clusters + (pl.has_super ? 1 : 0) : 0;
+                             ? pl.n_clusters + pl.n_super : 0;
         if (warp < n_cl) {
             const ClusterDev& cd = pl.cl[warp];
-            const double* dd = (warp == pl.n_clusters) ? pl.line_dS : pl.line_d;
+            const double* dd = pl.line_d[warp];
             double mk[kMom];
 #pragma unroll
             for (int k = 0; k < kMom; ++k) mk[k] = 0.0;
@@ -819,14 +845,24 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 if (!pl.series_on) {
                     lorentz_direct(sL2, 0, n_groups, lam, acc);
                 } else {
-                    lorentz_direct(sL2, 0, pl.g_direct_end, lam, acc);
-                    bool done = false;
-                    if (pl.has_super) {
-                        const ClusterW& cw = c.cw[pl.n_clusters];
-                        double cmin = cluster_cmin(cw, lam);
-                        if (cmin >= cw.thr) { cluster_series(cw, series_terms(cw.As / cmin), lam, acc); done = true; }
+                    // nested supersets {n >= n_k}, widest first: the first one that is far from
+                    // every pixel of the task absorbs all its lines; the few before it go direct
+                    const double lam_first = pl.wl[chunk * kChunk];     // uniform: nearest pixel when
+                    bool done = false;                                   // the task lies redward of c_bar
+                    for (int sidx = 0; sidx < pl.n_super && !done; ++sidx) {
+                        const int k = pl.n_clusters + sidx;
+                        const ClusterW& cw = c.cw[k];
+                        double cmin;
+                        if (lam_first >= cw.cb) { double u = lam_first - cw.cb; cmin = fma(u, u, cw.kcb2); }
+                        else cmin = cluster_cmin(cw, lam);
+                        if (cmin >= cw.thr) {
+                            lorentz_direct(sL2, 0, pl.cl[k].g_lo, lam, acc);
+                            cluster_series(cw, series_terms(cw.As / cmin), lam, acc);
+                            done = true;
+                        }
                     }
                     if (!done) {
+                        lorentz_direct(sL2, 0, pl.g_direct_end, lam, acc);
                         for (int k = 0; k < pl.n_clusters; ++k) {
                             const ClusterW& cw = c.cw[k];
                             double cmin = cluster_cmin(cw, lam);
@@ -1285,22 +1321,26 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
             pd.n_lines = d->balmer_n_lines;
             pd.n_lines_pad = (pd.n_lines + 3) & ~3;
             // far-field clusters over line-table indices; boundaries are multiples of 4 lines.
-            // For bc_lines_min = 3: direct n = 3..18 | 19..30 | 31..50 | 51..98 | 99..max, and the
-            // union of the four as the "super" cluster used by pixels far from the whole forest.
+            // For bc_lines_min = 3: base clusters n = 19..30 | 31..50 | 51..98 | 99..max (lines
+            // 3..18 always direct next to them) and nested supersets {n >= 7}, {n >= 11}, {n >= 19}
+            // for pixels far from the whole forest.
             pd.series_on = (!d->balmer_exact_line_sum && pd.line_type == SPAMM_LINE_LORENTZIAN) ? 1 : 0;
-            pd.n_clusters = 0; pd.has_super = 0; pd.g_direct_end = pd.n_lines_pad / 4;
+            pd.n_clusters = 0; pd.n_super = 0; pd.g_direct_end = pd.n_lines_pad / 4;
             {
                 const int bounds[5] = {16, 28, 48, 96, pd.n_lines_pad};
-                std::vector<double> dl(pd.n_lines_pad, 0.0), dS(pd.n_lines_pad, 0.0);
+                const int super_lo[3] = {4, 8, 16};
                 const double* cc = d->balmer_line_center;
-                auto make = [&](int lo, int hi, ClusterDev* out, std::vector<double>& dd) {
+                auto make = [&](int lo, int hi, int slot) -> int {
                     int hi_line = std::min(hi, pd.n_lines);            // exclude padding lines
                     double cmax = cc[lo], cmin = cc[lo];
                     for (int n = lo; n < hi_line; ++n) { cmax = std::max(cmax, cc[n]); cmin = std::min(cmin, cc[n]); }
+                    ClusterDev* out = &pd.cl[slot];
                     out->g_lo = lo / 4; out->g_hi = hi / 4;
                     out->cb0 = 0.5 * (cmax + cmin);
                     out->R0 = 0.5 * (cmax - cmin);
+                    std::vector<double> dd(pd.n_lines_pad, 0.0);
                     for (int n = lo; n < hi_line; ++n) dd[n] = (cc[n] - out->cb0) / out->R0;
+                    return upload(pl, dd.data(), dd.size(), &pd.line_d[slot]);
                 };
                 if (pd.series_on && pd.n_lines >= 32) {
                     pd.g_direct_end = bounds[0] / 4;
@@ -1308,19 +1348,18 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
                         int lo = bounds[b], hi = std::min(bounds[b + 1], pd.n_lines_pad);
                         if (lo >= pd.n_lines) break;
                         if (std::min(hi, pd.n_lines) - lo < 2) { hi = pd.n_lines_pad; }
-                        make(lo, hi, &pd.cl[pd.n_clusters], dl);
+                        if ((rc = make(lo, hi, pd.n_clusters))) return rc;
                         pd.n_clusters++;
                         if (hi == pd.n_lines_pad) break;
                     }
-                    if (pd.n_clusters > 1) {
-                        make(bounds[0], pd.n_lines_pad, &pd.cl[pd.n_clusters], dS);
-                        pd.has_super = 1;
+                    for (int sidx = 0; sidx < 3; ++sidx) {
+                        if (pd.n_lines - super_lo[sidx] < 8) continue;
+                        if ((rc = make(super_lo[sidx], pd.n_lines_pad, pd.n_clusters + pd.n_super))) return rc;
+                        pd.n_super++;
                     }
                 } else {
                     pd.series_on = 0;
                 }
-                if ((rc = upload(pl, dl.data(), dl.size(), &pd.line_d))) return rc;
-                if ((rc = upload(pl, dS.data(), dS.size(), &pd.line_dS))) return rc;
             }
             if ((rc = upload(pl, d->balmer_line_center, pd.n_lines, &pd.line_c0))) return rc;
             if ((rc = upload(pl, d->balmer_line_exparg, pd.n_lines, &pd.line_e))) return rc;
