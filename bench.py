@@ -59,57 +59,69 @@ FE_RANGES = ((1074.987, 3089.96), (3090.0, 3534.0), (3535.0, 7535.0))
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi sampled every 100 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons polled through NVML every 5 ms while the timed
+    region runs (the region lasts tens of milliseconds, too short for `nvidia-smi -lms`);
+    falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index=0):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.samples = []
+        self.stop_flag = False
+        self.thread = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), clk, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
-                continue
+        if self.nv is None:
             try:
-                c, cm, pw = float(parts[0]), float(parts[1]), float(parts[2])
-            except ValueError:
-                continue
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                sm.append(c)
-                smax.append(cm)
-                power.append(pw)
-                for n, v in zip(names, parts[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)),
-                "power_w_max": float(np.max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                     "--format=csv,noheader,nounits"], text=True).strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                        "reasons": ["NVML unavailable: single nvidia-smi sample after the run"]}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source available"]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
+            inside = self.samples[-3:]
+        reasons = set()
+        for _, _, _, rs in inside:
+            for n, bit in names.items():
+                if rs & bit:
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": float(smax),
+                "power_w_max": float(np.max([s[2] for s in inside])), "samples": len(inside),
+                "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------
@@ -257,7 +269,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     launches0 = plan.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
@@ -346,7 +358,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = max(4 * cores, 64)
+            n_cpu = max(16 * cores, 128)
             v, vals = cpu_pool_throughput(wl, np.asarray(model.data_spectrum.flux),
                                           np.asarray(model.data_spectrum.flux_error),
                                           params_host[:n_cpu], cores)

@@ -90,6 +90,12 @@ class Model(object):
     def invalidate_plan(self):
         self._plan = None
 
+    def __getstate__(self):
+        """Pickle without the device plan (rebuilt on demand after loading)."""
+        d = dict(self.__dict__)
+        d["_plan"] = None
+        return d
+
     # -- sampler -----------------------------------------------------------------------
     def initial_walkers(self, n_walkers):
         """Walker matrix drawn from the priors, component by component (Model.py:254-259)."""

@@ -88,10 +88,14 @@ class EnsembleSampler(object):
     # -- emcee-style accessors --------------------------------------------------
     @property
     def chain(self):
+        if "_chain_np" in self.__dict__:
+            return self._chain_np
         return None if self._chain is None else self._chain[:, :self.iterations, :].cpu().numpy()
 
     @property
     def lnprobability(self):
+        if "_lnprob_np" in self.__dict__:
+            return self._lnprob_np
         return None if self._lnprob is None else self._lnprob[:, :self.iterations].cpu().numpy()
 
     @property
@@ -101,11 +105,24 @@ class EnsembleSampler(object):
 
     @property
     def naccepted(self):
+        if "_nacc_np" in self.__dict__:
+            return self._nacc_np
         return self._nacc.cpu().numpy().astype(np.float64)
 
     @property
     def acceptance_fraction(self):
         return self.naccepted / max(self.iterations, 1)
+
+    def __getstate__(self):
+        """Pickle the results (chain, lnprobability, naccepted) as numpy arrays; device
+        buffers, the plan and the library handle stay behind."""
+        return {"k": self.k, "dim": self.dim, "a": self.a, "seed": self.seed,
+                "iterations": self.iterations, "_chain_np": self.chain,
+                "_lnprob_np": self.lnprobability,
+                "_nacc_np": None if self._nacc is None else self.naccepted}
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
 
     def reset(self):
         self.iterations = 0
