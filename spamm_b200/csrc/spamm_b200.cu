@@ -842,34 +842,45 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
 #pragma unroll
             for (int q = 0; q < kPix; ++q) lam[q] = pl.wl[i0 + 32 * q];
             if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
-                if (!pl.series_on) {
-                    lorentz_direct(sL2, 0, n_groups, lam, acc);
-                } else {
-                    // nested supersets {n >= n_k}, widest first: the first one that is far from
-                    // every pixel of the task absorbs all its lines; the few before it go direct
-                    const double lam_first = pl.wl[chunk * kChunk];     // uniform: nearest pixel when
-                    bool done = false;                                   // the task lies redward of c_bar
-                    for (int sidx = 0; sidx < pl.n_super && !done; ++sidx) {
-                        const int k = pl.n_clusters + sidx;
-                        const ClusterW& cw = c.cw[k];
+                // The line sum is a short list of segments, each either a run of line groups summed
+                // directly or one cluster summed by its far-field series (one instance of each body):
+                //   exact mode            : [direct 0..n_groups)
+                //   a far nested superset : [direct 0..g_lo(s)) [series s]
+                //   otherwise             : [direct 0..g_direct_end) then per base cluster series|direct
+                int sup = -1, nseg = 1;
+                double sup_cmin = 0.0;
+                if (pl.series_on) {
+                    // nested supersets {n >= n_k}, widest first: the first one that is far from every
+                    // pixel of the task absorbs all its lines
+                    const double lam_first = pl.wl[chunk * kChunk];     // uniform: the nearest pixel when
+                    for (int sidx = 0; sidx < pl.n_super && sup < 0; ++sidx) {   // the task is redward of c_bar
+                        const ClusterW& cw = c.cw[pl.n_clusters + sidx];
                         double cmin;
                         if (lam_first >= cw.cb) { double u = lam_first - cw.cb; cmin = fma(u, u, cw.kcb2); }
                         else cmin = cluster_cmin(cw, lam);
-                        if (cmin >= cw.thr) {
-                            lorentz_direct(sL2, 0, pl.cl[k].g_lo, lam, acc);
-                            cluster_series(cw, series_terms(cw.As / cmin), lam, acc);
-                            done = true;
+                        if (cmin >= cw.thr) { sup = pl.n_clusters + sidx; sup_cmin = cmin; }
+                    }
+                    nseg = sup >= 0 ? 2 : 1 + pl.n_clusters;
+                }
+#pragma unroll 1
+                for (int sg = 0; sg < nseg; ++sg) {
+                    int g0 = 0, g1 = n_groups, kc = 0;
+                    double cmin = 0.0;
+                    bool series = false;
+                    if (pl.series_on) {
+                        if (sg == 0) {
+                            g1 = sup >= 0 ? pl.cl[sup].g_lo : pl.g_direct_end;
+                        } else if (sup >= 0) {
+                            kc = sup; cmin = sup_cmin; series = true;
+                        } else {
+                            kc = sg - 1;
+                            cmin = cluster_cmin(c.cw[kc], lam);
+                            series = cmin >= c.cw[kc].thr;
+                            g0 = pl.cl[kc].g_lo; g1 = pl.cl[kc].g_hi;
                         }
                     }
-                    if (!done) {
-                        lorentz_direct(sL2, 0, pl.g_direct_end, lam, acc);
-                        for (int k = 0; k < pl.n_clusters; ++k) {
-                            const ClusterW& cw = c.cw[k];
-                            double cmin = cluster_cmin(cw, lam);
-                            if (cmin >= cw.thr) cluster_series(cw, series_terms(cw.As / cmin), lam, acc);
-                            else lorentz_direct(sL2, pl.cl[k].g_lo, pl.cl[k].g_hi, lam, acc);
-                        }
-                    }
+                    if (series) cluster_series(c.cw[kc], series_terms(c.cw[kc].As / cmin), lam, acc);
+                    else lorentz_direct(sL2, g0, g1, lam, acc);
                 }
             } else {
                 for (int n = 0; n < n_lines; ++n) {

@@ -60,7 +60,7 @@ class ModelPlan(object):
         if bounds is not None:
             lo, hi = list(bounds[0]), list(bounds[1])
             assert len(lo) == self.n_dim and len(hi) == self.n_dim
-        if with_priors:
+        if with_priors or bounds is not None:
             for v in lo + hi:
                 if isinstance(v, str):
                     raise TypeError("prior bound %r is unresolved; call initial_values(spectrum) "

@@ -267,3 +267,84 @@ def test_lnposterior_exact_line_sum_mode_agrees():
     a, b = m.lnposterior_batch(c.params), m2.lnposterior_batch(c.params)
     assert rel_err(a, b).max() < 1e-12
     assert rel_err(b, c.lnpost).max() < LNPOST_RTOL
+
+
+@pytest.mark.parametrize("name,W", [("cfg2_nc_fe", 1024), ("cfg3_nc_hg", 2048), ("cfg4_nc_bc", 4096)])
+def test_baseline_configs_at_full_walker_counts(name, W):
+    """BASELINE.json configs 2-4 at their quoted walker counts: a slice against the oracle,
+    everything else through size-independent properties."""
+    from oracle.spamm_numpy import OracleModel
+    z, _ = lnpost_cases()
+    c = Case(z, name)
+    m = _model(c)
+    m.max_walkers = W
+    rng = np.random.RandomState(len(name))
+    lo, hi = c.lo, c.hi
+    params = lo + (hi - lo) * rng.rand(W, len(lo))
+    got = m.lnposterior_batch(params)
+    assert got.shape == (W,) and np.all(np.isfinite(got))
+    assert np.array_equal(got, m.lnposterior_batch(params))
+    o = OracleModel(c.wl, c.flux, c.err, comps=c.comps, bc=c.bc, bpc=c.bpc)
+    pick = rng.choice(W, 6, replace=False)
+    want = o.ln_posterior_batch(params[pick])
+    assert rel_err(got[pick], want).max() < LNPOST_RTOL
+    # a walker moved just outside any one bound is rejected without touching the rest
+    D_CHECK = min(len(lo), 8)
+    bad = params[:D_CHECK].copy()
+    for j in range(D_CHECK):
+        bad[j, j] = hi[j]
+    res = m.lnposterior_batch(np.concatenate([bad, params[D_CHECK:64]]))
+    assert np.all(np.isneginf(res[:D_CHECK])) and np.array_equal(res[D_CHECK:], got[D_CHECK:64])
+
+
+def test_reference_test_grid_18000_pixels():
+    """parameters.yaml testing grid: np.arange(1000, 10000, 0.5), all components."""
+    from oracle.spamm_numpy import OracleModel
+    wl = np.arange(1000, 10000, 0.5)
+    comps = ["PL", "FE", "HOST", "BC"]
+    o0 = OracleModel(wl, wl, wl, comps=comps)
+    fl = [o0.component_flux(cn, TRUTH[cn]) for cn in comps]
+    d = np.sum(fl, axis=0)
+    e = np.sqrt(np.sum([(0.05 * f) ** 2 for f in fl], axis=0))
+    o = OracleModel(wl, d, e, comps=comps)
+    np.random.seed(42)
+    params = np.array([o.initial_values() for _ in range(48)])
+    params[0] = np.concatenate([TRUTH[cn] for cn in comps])
+    c = Case.__new__(Case)
+    c.wl, c.flux, c.err, c.comps, c.bc, c.bpc = wl, d, e, comps, True, True
+    m = _model(c)
+    got = m.lnposterior_batch(params)
+    want = o.ln_posterior_batch(params[:5])
+    assert rel_err(got[:5], want).max() < LNPOST_RTOL
+    assert abs(got[0] - 6.087254312300e+05) < 1e-5 * 6.09e5      # SURVEY.md App. C3 probe value
+    assert m.plan.status() == 0
+
+
+def test_tiny_and_odd_sized_spectra():
+    """P not a multiple of the 64-pixel warp task, P smaller than one task, spectra entirely
+    blueward / redward of the Balmer edge."""
+    from oracle.spamm_numpy import OracleModel
+    rng = np.random.RandomState(3)
+    for wl in (np.linspace(3000., 4500., 37), np.linspace(1200., 3300., 333), np.linspace(3800., 9000., 1001)):
+        comps = ["PL", "FE", "HOST", "BC"]
+        o0 = OracleModel(wl, wl, wl, comps=comps)
+        fl = [o0.component_flux(cn, TRUTH[cn]) for cn in comps]
+        d = np.sum(fl, axis=0) * (1 + 0.01 * rng.standard_normal(len(wl)))
+        e = 0.05 * np.abs(d) + 1e-18
+        lo = np.array([0, -3, 0, 0, 0, 901, 0, 0, 0, 0, 0, 0, 0, 30, 0, 500, 0, -10, 100, 2], dtype=float)
+        hi = np.array([1e-13, 3, 1e-13, 1e-13, 1e-13, 1e4, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e3,
+                       1e-13, 1e5, 2, 10, 1e4, 9], dtype=float)
+        params = lo + (hi - lo) * rng.rand(12, 20)
+        o = OracleModel(wl, d, e, comps=comps)
+        o.set_bounds(lo, hi)
+        with np.errstate(all="ignore"):
+            want = o.ln_posterior_batch(params)
+        from spamm_b200.plan import ModelPlan
+        from spamm_b200.Spectrum import Spectrum
+        sp = Spectrum(wl, d, e)
+        cs = _components(comps)
+        for cc in cs:
+            cc.initialize(sp)
+        plan = ModelPlan(cs, sp, with_priors=False, bounds=(lo, hi), max_walkers=16)
+        got = plan.lnposterior_host(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL, (len(wl), got, want)
