@@ -45,7 +45,10 @@ static int set_error(int code, const std::string& msg) {
 // ---------------------------------------------------------------------------
 // device-side plan
 // ---------------------------------------------------------------------------
-constexpr int kThreads = 256;          // threads per CTA of the fused kernel
+#ifndef SPAMM_THREADS
+#define SPAMM_THREADS 256
+#endif
+constexpr int kThreads = SPAMM_THREADS;  // threads per CTA of the fused kernel
 #ifndef SPAMM_PIX
 #define SPAMM_PIX 2
 #endif
@@ -364,7 +367,8 @@ __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) 
 // bc_K[k] = 2 h nu^3 c_AA / (c_cgs^2 lambda^2) is the walker-independent factor of B_lambda.
 __device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double tauBE) {
     double log_boltz = pl.bc_hnu[k] / kT;
-    double boltzm1 = expm1(log_boltz);
+    // expm1(x): for x >= 0.5 (T < 8e4 K at 3646 A) exp(x) - 1 loses at most one bit
+    double boltzm1 = log_boltz >= 0.5 ? exp_fast(log_boltz) - 1.0 : expm1(log_boltz);
     double flam = pl.bc_K[k] / boltzm1;
     double tau = tauBE * pl.bc_t3[k];
     double absorption = 1 - exp_fast(-tau);
@@ -419,13 +423,13 @@ __device__ int nearest_index_guess(const double* __restrict__ wl, int n, double 
 }
 
 // NuclearContinuumComponent.flux at pixel i (NC:176-201)
-__device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i) {
+__device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i, double hi, double lo) {
     if (!pl.nc_broken) {
-        // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x held in
+        // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x (hi, lo) held in
         // double-double, so the result is within ~1 ulp of pow()
-        double s = -c.nc_slope1, hi = pl.nc_lnx_hi[i];
+        double s = -c.nc_slope1;
         double th = s * hi;
-        double tl = fma(s, hi, -th) + s * pl.nc_lnx_lo[i];
+        double tl = fma(s, hi, -th) + s * lo;
         double v = exp_fast(th);
         v = fma(v, tl, v);
         return c.nc_norm * v;
@@ -812,8 +816,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
         const int i0 = chunk * kChunk + lane;
         double m[kPix], post[kPix], acc[kPix];
+        // every global load of the task is issued here, ahead of its first use, so one L2 round
+        // trip is exposed per task instead of one per phase
+        double lnhi[kPix], lnlo[kPix], lam[kPix], dat[kPix], ierr[kPix];
 #pragma unroll
-        for (int q = 0; q < kPix; ++q) acc[q] = 0.0;
+        for (int q = 0; q < kPix; ++q) {
+            acc[q] = 0.0;
+            lnhi[q] = off_nc >= 0 ? pl.nc_lnx_hi[i0 + 32 * q] : 0.0;
+            lnlo[q] = off_nc >= 0 ? pl.nc_lnx_lo[i0 + 32 * q] : 0.0;
+            lam[q] = pl.wl[i0 + 32 * q];
+            dat[q] = MODE == 0 ? pl.flux[i0 + 32 * q] : 0.0;
+            ierr[q] = MODE == 0 ? pl.inv_err[i0 + 32 * q] : 0.0;
+        }
         {
             // component values, then summed in Model.components order (Model.py:353-364):
             // m = everything listed before the Balmer component, post = everything after it
@@ -822,7 +836,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
 #pragma unroll
             for (int q = 0; q < kPix; ++q) {
-                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, i0 + 32 * q) : 0.0;
+                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, i0 + 32 * q, lnhi[q], lnlo[q]) : 0.0;
                 m[q] = 0.0;
                 post[q] = 0.0;
             }
@@ -838,9 +852,6 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
         }
         if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
-            double lam[kPix];
-#pragma unroll
-            for (int q = 0; q < kPix; ++q) lam[q] = pl.wl[i0 + 32 * q];
             if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
                 // The line sum is a short list of segments, each either a run of line groups summed
                 // directly or one cluster summed by its far-field series (one instance of each body):
@@ -909,7 +920,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             if (q_bal + 1 < pl.n_comp) v = v + post[q];
             const bool live = i < P;
             if (MODE == 0) {
-                double r = (pl.flux[i] - v) * pl.inv_err[i];                                   // Model.py:440
+                double r = (dat[q] - v) * ierr[q];                                              // Model.py:440
                 if (live) chi += r * r;
             } else if (live) {
                 fout[i] = v;
