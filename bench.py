@@ -246,8 +246,27 @@ def run_ours(args):
     lnp = torch.empty(n_local, dtype=torch.float64, device=dev)
     gathered = torch.empty(n_local * world, dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    exchange = "none"
+    p2p = None
+    if world > 1:
+        from spamm_b200.distributed import P2PLnPost
+        exchange = "nccl all_gather"
+        if args.exchange == "p2p" and P2PLnPost.available():
+            try:
+                p2p = P2PLnPost(plan, max_n=n_local * world)
+                exchange = "P2P stores from the compute kernel into every peer's symmetric buffer + barrier"
+            except Exception as exc:                                  # symmetric memory unavailable
+                p2p = None
+                exchange = "nccl all_gather (p2p unavailable: %s)" % type(exc).__name__
+    p2p_step = [0]
 
     def step():
+        if p2p is not None:
+            k = p2p_step[0] & 1
+            p2p_step[0] += 1
+            plan.lnposterior_p2p(params, p2p.hdls[k].buffer_ptrs_dev, world, rank * n_local)
+            p2p.hdls[k].barrier(channel=0)
+            return
         plan.lnposterior(params, out=lnp)
         if world > 1:
             dist.all_gather_into_tensor(gathered, lnp)
@@ -304,6 +323,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_e2e = float(t.item())
     e2e_value = n_local * world * e2e_steps / t_e2e
+    if p2p is not None:
+        # every rank's buffer holds the whole gathered vector; this rank's slice must equal
+        # what the plain local call returns
+        got = p2p.bufs[(p2p_step[0] - 1) & 1][rank * n_local:(rank + 1) * n_local].cpu().numpy()
+        plan.lnposterior(params, out=lnp)
+        assert np.array_equal(got, lnp.cpu().numpy()), "P2P-exchanged results differ from the local call"
     assert np.array_equal(res, lnp.cpu().numpy()), "host-buffer and device-buffer paths disagree"
 
     value = n_local * world * args.steps / (total_ms * 1e-3)
@@ -374,8 +399,7 @@ def run_ours(args):
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config5: full NC+Fe+HG+BC, 8192 px, D=20, walkers from priors (seed 42)",
                        "walkers_per_gpu": n_local, "walkers_total": n_local * world, "n_pix": N_PIX,
-                       "l2": "256 MiB flush between timed steps", "parallelism": "walkers sharded x%d, "
-                       "all-gather of ln-probs per step" % world,
+                       "l2": "256 MiB flush between timed steps", "parallelism": "walkers sharded x%d" % world, "exchange": exchange,
                        "template_mode": "bank" if plan.template_mode == _lib.TEMPLATES_BANK else "direct"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_host.nbytes),
@@ -400,6 +424,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: how per-walker ln-probs reach every rank")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

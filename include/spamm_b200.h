@@ -136,6 +136,15 @@ void spamm_plan_destroy(SpammPlan* plan);
 int spamm_lnpost_batch(SpammPlan* plan, const double* params_dev, int32_t n_walkers,
                        double* lnp_dev, void* stream);
 
+/* Multi-GPU variant with the result exchange fused into the kernel: walker w's ln-posterior
+ * is stored at element (elem_offset + w) of EVERY buffer in peer_bufs_dev[0..n_peers) -- the
+ * symmetric, peer-mapped buffers of all ranks (this rank included) -- by P2P stores over
+ * NVLink, so no all-gather copy follows; the caller only needs a cross-rank barrier before it
+ * reads its own buffer.  Replaces the result gather of emcee's pool.map (Model.py:267-286). */
+int spamm_lnpost_batch_p2p(SpammPlan* plan, const double* params_dev, int32_t n_walkers,
+                           const uint64_t* peer_bufs_dev, int32_t n_peers, int64_t elem_offset,
+                           void* stream);
+
 /* Same call with HOST buffers: pinned staging, H2D, kernel, D2H, synchronise.
  * This is what an emcee `pool.map` adapter binds (Model.py:283-289). */
 int spamm_lnpost_batch_host(SpammPlan* plan, const double* params_host, int32_t n_walkers,

@@ -348,6 +348,21 @@ struct TemplCoef {
     double a;          // norm_t / nf
 };
 
+// Multi-GPU result exchange fused into the kernel: instead of writing lnp[w] locally and
+// all-gathering afterwards, the finishing thread stores the value straight into every peer's
+// symmetric buffer over NVLink (P2P stores); bufs == nullptr selects the plain local store.
+struct PeerOut {
+    const unsigned long long* bufs;   // device array of n_peers base pointers (incl. this rank)
+    int n_peers;
+    long long offset;                 // element offset of this launch's walker 0 in the gathered vector
+};
+
+__device__ __forceinline__ void store_result(double* out, int w, double v, const PeerOut& po) {
+    if (po.bufs == nullptr) { out[w] = v; return; }
+    for (int r = 0; r < po.n_peers; ++r)
+        reinterpret_cast<double*>(po.bufs[r])[po.offset + w] = v;
+}
+
 // Storey & Hummer table look-up: kx=ky=1 FITPACK spline == clamped bilinear
 __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) {
     double x = fmin(fmax(n_e, pl.sh_ne[0]), pl.sh_ne[SPAMM_SH95_NE - 1]);
@@ -562,7 +577,7 @@ constexpr int kChunk = 32 * kPix;      // pixels per warp task
 template <int MODE>   // 0: ln-posterior; 1: model flux out
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
-          uint32_t mask, DirectRows dr) {
+          uint32_t mask, DirectRows dr, PeerOut po) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WalkerCtx& c = *reinterpret_cast<WalkerCtx*>(smem_raw);
     double* sLine = reinterpret_cast<double*>(smem_raw + sizeof(WalkerCtx));   // [n_pad/4][12] grouped
@@ -589,7 +604,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     __syncthreads();
     if (MODE == 0 && !c.prior_ok) {       // ln_posterior returns -inf before any flux (Model.py:67-69)
-        if (tid == 0) out[w] = -CUDART_INF;
+        if (tid == 0) store_result(out, w, -CUDART_INF, po);
         return;
     }
 
@@ -941,7 +956,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) {
                 double ln_l = -0.5 * (s + pl.sum_ln);
-                out[w] = nan_to_num(ln_l) + 0.0;      // + ln_prior (== 0 inside the box)
+                store_result(out, w, nan_to_num(ln_l) + 0.0, po);      // + ln_prior (== 0 inside the box)
             }
         }
     }
@@ -1537,7 +1552,8 @@ static int direct_rows_for_chunk(SpammPlan* pl, const TemplDev& ts, const double
 
 template <int MODE>
 static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
-                          double* out_dev, cudaStream_t st, bool force_direct) {
+                          double* out_dev, cudaStream_t st, bool force_direct,
+                          PeerOut po = PeerOut{nullptr, 0, 0}) {
     const PlanDev& pd = pl->dev;
     bool need_fe = false, need_host = false;
     for (int q = 0; q < pd.n_comp; ++q) {
@@ -1548,7 +1564,7 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
     bool direct = (need_fe || need_host) && (force_direct || pl->template_mode == SPAMM_TEMPLATES_DIRECT);
     if (!direct) {
         DirectRows dr{nullptr, nullptr, nullptr, nullptr};
-        k_walkers<MODE><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr);
+        k_walkers<MODE><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
         pl->launches += 1;
         CUDA_TRY(cudaGetLastError());
         return SPAMM_OK;
@@ -1567,7 +1583,7 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
             dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
         }
         double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
-        k_walkers<MODE><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr);
+        k_walkers<MODE><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
         pl->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1583,6 +1599,17 @@ extern "C" int spamm_lnpost_batch(SpammPlan* pl, const double* params_dev, int32
     if (n_walkers == 0) return SPAMM_OK;
     if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
     return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, lnp_dev, (cudaStream_t)stream, false);
+}
+
+extern "C" int spamm_lnpost_batch_p2p(SpammPlan* pl, const double* params_dev, int32_t n_walkers,
+                                      const uint64_t* peer_bufs_dev, int32_t n_peers, int64_t elem_offset,
+                                      void* stream) {
+    if (!pl || !params_dev || !peer_bufs_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_walkers < 0 || n_peers < 1 || elem_offset < 0) return set_error(SPAMM_EINVAL, "bad argument");
+    if (n_walkers == 0) return SPAMM_OK;
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    PeerOut po{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), n_peers, (long long)elem_offset};
+    return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, nullptr, (cudaStream_t)stream, false, po);
 }
 
 extern "C" int spamm_lnpost_batch_host(SpammPlan* pl, const double* params_host, int32_t n_walkers,

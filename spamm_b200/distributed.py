@@ -78,3 +78,52 @@ class ShardedLnPost(object):
             lo, hi, _ = shard_bounds(n, self.world, r)
             parts.append(self._buf[r * per:r * per + (hi - lo)])
         return torch.cat(parts)
+
+
+class P2PLnPost(object):
+    """ShardedLnPost with the exchange fused into the compute kernel.
+
+    Every rank owns a symmetric (peer-mapped) result buffer; the fused walker kernel stores each
+    ln-posterior directly into all peers' buffers over NVLink (`spamm_lnpost_batch_p2p`), so the
+    only thing left after the kernel is a cross-rank barrier on the symmetric-memory signal pads --
+    no all-gather copy.  Two buffers alternate so a fast rank's next half-step never overwrites
+    values a slower rank is still reading (each step ends in a barrier, so ranks are never more
+    than one step apart)."""
+
+    def __init__(self, plan, max_n, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.plan = plan
+        self.rank, self.world = world_info()
+        self.group = group if group is not None else dist.group.WORLD
+        self.max_n = int(max_n)
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm.empty(self.max_n, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+            t.fill_(float("nan"))
+            h = symm.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.hdls.append(h)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        self.step = 0
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+        except Exception:
+            return False
+
+    def __call__(self, params):
+        n = params.shape[0]
+        if n > self.max_n:
+            raise ValueError("P2PLnPost buffer holds %d walkers, got %d" % (self.max_n, n))
+        k = self.step & 1
+        self.step += 1
+        buf, hdl = self.bufs[k], self.hdls[k]
+        lo, hi, _ = shard_bounds(n, self.world, self.rank)
+        if hi > lo:
+            self.plan.lnposterior_p2p(params[lo:hi].contiguous(), hdl.buffer_ptrs_dev, self.world, lo)
+        hdl.barrier(channel=0)
+        return buf[:n]

@@ -119,6 +119,14 @@ class ModelPlan(object):
                                                ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def lnposterior_p2p(self, params, peer_bufs_dev, n_peers, elem_offset):
+        """Evaluate [W, D] walkers and store each result at elem_offset + w of every peer
+        buffer (device array of n_peers pointers); see spamm_lnpost_batch_p2p."""
+        self._check_params(params)
+        _lib.check(self.lib.spamm_lnpost_batch_p2p(self._h, ctypes.c_void_p(params.data_ptr()),
+                                                   params.shape[0], ctypes.c_void_p(int(peer_bufs_dev)),
+                                                   int(n_peers), int(elem_offset), self._stream()))
+
     def model_flux(self, params, mask=None, out=None):
         """[W, D] -> model flux [W, P] of the components selected by `mask` (all by default)."""
         torch = _torch()

@@ -82,8 +82,20 @@ class EnsembleSampler(object):
         self._walkers = None
         self._lnp = None
         self._nacc = None
-        from .distributed import ShardedLnPost
-        self._evaluate = ShardedLnPost(self.plan.lnposterior)
+        # multi-GPU: each rank evaluates its slice; results reach every rank either by P2P stores
+        # from the compute kernel (symmetric memory + barrier) or, as a fallback, an NCCL all-gather
+        import os
+        from .distributed import ShardedLnPost, P2PLnPost, world_info
+        self.exchange = "single"
+        if world_info()[1] > 1:
+            if os.environ.get("SPAMM_EXCHANGE", "p2p") == "p2p" and P2PLnPost.available():
+                self._evaluate = P2PLnPost(self.plan, max_n=nwalkers)
+                self.exchange = "p2p"
+            else:
+                self._evaluate = ShardedLnPost(self.plan.lnposterior)
+                self.exchange = "nccl"
+        else:
+            self._evaluate = ShardedLnPost(self.plan.lnposterior)
 
     # -- emcee-style accessors --------------------------------------------------
     @property

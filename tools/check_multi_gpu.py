@@ -25,6 +25,11 @@ sharded = ShardedLnPost(plan.lnposterior)(d).cpu().numpy()
 assert np.array_equal(full, sharded), "sharded evaluation differs from the single-rank one"
 
 s = EnsembleSampler(nwalkers=256, dim=20, lnpostfn=ln_posterior, args=[model], seed=7)
+if rank == 0:
+    print("exchange:", s.exchange)
+if s.exchange == "p2p":
+    g = s._evaluate(d).clone()
+    assert np.array_equal(g.cpu().numpy(), full), "P2P-exchanged evaluation differs"
 s.run_mcmc(params, 30)
 chain = torch.from_numpy(s.chain).cuda()
 ref = chain.clone()
