@@ -722,17 +722,28 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     __syncthreads();
 
-    // ---- P2: the serial ratio recursion (one lane) overlapped with the f0 stage (the rest) ---
-    if (tid == 0) {
-        if (do_bpc) {
-            // flux_ratios[i] = flux_ratios[i-1] * exp(...)  sequentially, BC:292-296
-            double prev = 0.0;    // flux_ratios[-1] of the zero-initialised array
-            for (int n = 0; n < n_lines; ++n) {
-                if (pl.line_min + n <= 50) prev = sG[n];
-                else { prev = prev * sG[n]; sG[n] = prev; }
-            }
+    // ---- P2: ratio recursion flux_ratios[i] = flux_ratios[i-1] * exp(...) for n > 50 (BC:292-296)
+    // as a warp-parallel prefix product: each lane multiplies its contiguous segment, an exclusive
+    // multiplicative scan over the 32 segment totals supplies the carry (same factors as the
+    // sequential loop, re-associated: a few ulp)
+    if (warp == 0 && do_bpc) {
+        const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
+        const int cnt = n_lines - n50, per = (cnt + 31) / 32;
+        const int lo = n50 + lane * per, hi = min(lo + per, n_lines);
+        double tot = 1.0;
+        for (int n = lo; n < hi; ++n) tot *= sG[n];
+        double incl = tot;
+        for (int o = 1; o < 32; o <<= 1) {
+            double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
         }
-    } else if (do_bc && tid >= 32) {
+        double carry = __shfl_up_sync(0xffffffffu, incl, 1);
+        const double seed = n50 > 0 ? sG[n50 - 1] : 0.0;              // flux_ratios[-1] of a zeroed array
+        double run = lane == 0 ? seed : seed * carry;
+        __syncwarp();
+        for (int n = lo; n < hi; ++n) { run *= sG[n]; sG[n] = run; }
+    }
+    if (do_bc && tid >= 32) {
         const double tauBE = b_tau;
         int nst = min(pl.bc_nstage, P);
         for (int k = tid - 32; k < nst; k += kThreads - 32) sF0[k] = bc_f0(pl, k, kT, tauBE);
