@@ -574,7 +574,10 @@ __device__ __forceinline__ int series_terms(double rho2) {
 #endif
 constexpr int kChunk = 32 * kPix;      // pixels per warp task
 
-template <int MODE>   // 0: ln-posterior; 1: model flux out
+// MODE 0: ln-posterior, 1: model flux out.  CANON: the live components are in the reference's
+// canonical order with the Balmer component last (run_spamm.py:100-122), so the model is
+// ((NC + Fe) + host) + Balmer and no per-component ordering state is carried through the task.
+template <int MODE, bool CANON>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
           uint32_t mask, DirectRows dr, PeerOut po) {
@@ -848,6 +851,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
             acc[q] = 0.0;
+            post[q] = 0.0;
             lnhi[q] = off_nc >= 0 ? pl.nc_lnx_hi[i0 + 32 * q] : 0.0;
             lnlo[q] = off_nc >= 0 ? pl.nc_lnx_lo[i0 + 32 * q] : 0.0;
             lam[q] = pl.wl[i0 + 32 * q];
@@ -855,25 +859,36 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             ierr[q] = MODE == 0 ? pl.inv_err[i0 + 32 * q] : 0.0;
         }
         {
-            // component values, then summed in Model.components order (Model.py:353-364):
-            // m = everything listed before the Balmer component, post = everything after it
             double fe_v[kPix], host_v[kPix], nc_v[kPix];
             if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
             if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
 #pragma unroll
-            for (int q = 0; q < kPix; ++q) {
+            for (int q = 0; q < kPix; ++q)
                 nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, i0 + 32 * q, lnhi[q], lnlo[q]) : 0.0;
-                m[q] = 0.0;
-                post[q] = 0.0;
-            }
-            for (int k = 0; k < pl.n_comp; ++k) {
-                if (!((mask >> k) & 1u) || k == q_bal) continue;
-                const int kind = pl.comp_kind[k];
+            if (CANON) {
+                // model_spectrum.flux starts at zero and adds NC, Fe, host in turn (Model.py:350-380)
 #pragma unroll
                 for (int q = 0; q < kPix; ++q) {
-                    const double v = kind == SPAMM_COMP_NUCLEAR ? nc_v[q]
-                                     : (kind == SPAMM_COMP_FE ? fe_v[q] : host_v[q]);
-                    if (k < q_bal) m[q] = m[q] + v; else post[q] = post[q] + v;
+                    double v = 0.0;
+                    if (off_nc >= 0) v = v + nc_v[q];
+                    if (n_fe) v = v + fe_v[q];
+                    if (n_host) v = v + host_v[q];
+                    m[q] = v;
+                }
+            } else {
+                // component values summed in Model.components order (Model.py:353-364):
+                // m = everything listed before the Balmer component, post = everything after it
+#pragma unroll
+                for (int q = 0; q < kPix; ++q) m[q] = 0.0;
+                for (int k = 0; k < pl.n_comp; ++k) {
+                    if (!((mask >> k) & 1u) || k == q_bal) continue;
+                    const int kind = pl.comp_kind[k];
+#pragma unroll
+                    for (int q = 0; q < kPix; ++q) {
+                        const double v = kind == SPAMM_COMP_NUCLEAR ? nc_v[q]
+                                         : (kind == SPAMM_COMP_FE ? fe_v[q] : host_v[q]);
+                        if (k < q_bal) m[q] = m[q] + v; else post[q] = post[q] + v;
+                    }
                 }
             }
         }
@@ -943,7 +958,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 if (do_bpc) bpc = ((i > bpc_istar) ? acc[q] : 0.0) * bpc_scale;                // BC:386-387
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
-            if (q_bal + 1 < pl.n_comp) v = v + post[q];
+            if (!CANON && q_bal + 1 < pl.n_comp) v = v + post[q];
             const bool live = i < P;
             if (MODE == 0) {
                 double r = (dat[q] - v) * ierr[q];                                              // Model.py:440
@@ -1488,8 +1503,10 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.n_chunks + pd.bc_nstage) * sizeof(double);
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
     CUDA_TRY(cudaDeviceSynchronize());
     return SPAMM_OK;
 }
@@ -1561,6 +1578,17 @@ static int direct_rows_for_chunk(SpammPlan* pl, const TemplDev& ts, const double
                     d_f, d_nf, st);
 }
 
+// canonical = live components appear as NC < Fe < host < Balmer in the list
+static bool canonical_order(const PlanDev& pd, uint32_t mask) {
+    int last = -1;
+    for (int q = 0; q < pd.n_comp; ++q) {
+        if (!((mask >> q) & 1u)) continue;
+        if (pd.comp_kind[q] < last) return false;
+        last = pd.comp_kind[q];
+    }
+    return true;
+}
+
 template <int MODE>
 static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
                           double* out_dev, cudaStream_t st, bool force_direct,
@@ -1575,7 +1603,10 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
     bool direct = (need_fe || need_host) && (force_direct || pl->template_mode == SPAMM_TEMPLATES_DIRECT);
     if (!direct) {
         DirectRows dr{nullptr, nullptr, nullptr, nullptr};
-        k_walkers<MODE><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
+        if (canonical_order(pd, mask))
+            k_walkers<MODE, true><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
+        else
+            k_walkers<MODE, false><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
         pl->launches += 1;
         CUDA_TRY(cudaGetLastError());
         return SPAMM_OK;
@@ -1594,7 +1625,10 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
             dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
         }
         double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
-        k_walkers<MODE><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
+        if (canonical_order(pd, mask))
+            k_walkers<MODE, true><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
+        else
+            k_walkers<MODE, false><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
         pl->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
