@@ -348,3 +348,24 @@ def test_tiny_and_odd_sized_spectra():
         plan = ModelPlan(cs, sp, with_priors=False, bounds=(lo, hi), max_walkers=16)
         got = plan.lnposterior_host(params)
         assert rel_err(got, want).max() < LNPOST_RTOL, (len(wl), got, want)
+
+
+def test_non_canonical_component_order():
+    """Model.components order fixes the parameter layout and the summation order
+    (Model.py:353-364); an order other than run_spamm's PL, FE, HOST, BC takes the generic kernel."""
+    from oracle.spamm_numpy import OracleModel
+    z, _ = lnpost_cases()
+    c = Case(z, "full_fp6")
+    for comps in (["HOST", "BC", "PL", "FE"], ["BC", "PL"], ["FE", "PL"]):
+        o = OracleModel(c.wl, c.flux, c.err, comps=comps)
+        np.random.seed(11)
+        params = np.array([o.initial_values() for _ in range(10)])
+        want = o.ln_posterior_batch(params)
+        cc = Case.__new__(Case)
+        cc.wl, cc.flux, cc.err, cc.comps, cc.bc, cc.bpc = c.wl, c.flux, c.err, comps, True, True
+        m = _model(cc)
+        got = m.lnposterior_batch(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL, comps
+        f = m.model_flux_batch(params[:2])
+        wantf = np.array([o.model_flux(p) for p in params[:2]])
+        assert np.max(np.abs(f - wantf)) <= FLUX_RTOL * np.max(np.abs(wantf))
