@@ -312,12 +312,17 @@ def run_ours(args):
 
     # end to end through the public API with host buffers (H2D + kernel + D2H every step)
     e2e_steps = max(3, min(args.steps, 10))
-    model.lnposterior_batch(params_host)
+    pin_in = torch.empty(params_host.shape, dtype=torch.float64, pin_memory=True)
+    pin_out = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+    pin_in.numpy()[...] = params_host                 # the step's inputs live in pinned host memory
+    h_in, h_out = pin_in.numpy(), pin_out.numpy()
+    model.lnposterior_batch(h_in, out=h_out)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = model.lnposterior_batch(params_host)
+        res = model.lnposterior_batch(h_in, out=h_out)      # H2D + kernel + D2H + sync, every step
     t_e2e = time.perf_counter() - t0
+    res = np.array(res)
     if world > 1:
         t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

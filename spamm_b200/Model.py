@@ -154,6 +154,7 @@ class Model(object):
             p = p[component.parameter_count:]
         return ln_p
 
-    def lnposterior_batch(self, params):
-        """ln-posterior of a whole walker ensemble in one call: numpy [W, D] -> numpy [W]."""
-        return self.plan.lnposterior_host(params)
+    def lnposterior_batch(self, params, out=None):
+        """ln-posterior of a whole walker ensemble in one call: numpy [W, D] -> numpy [W]
+        (`out`: optional preallocated result array; page-locked buffers avoid a staging copy)."""
+        return self.plan.lnposterior_host(params, out=out)

@@ -1672,16 +1672,26 @@ extern "C" int spamm_lnpost_batch_host(SpammPlan* pl, const double* params_host,
         CUDA_TRY(cudaMalloc(&pl->d_lnp, (size_t)pl->max_walkers * sizeof(double)));
     }
     cudaStream_t st = pl->own_stream;
+    // caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch
+    // pin_memory) are copied from/to directly; pageable ones go through the plan's pinned staging
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool pin_in = is_pinned(params_host), pin_out = is_pinned(lnp_host);
     for (int w0 = 0; w0 < n_walkers; w0 += pl->max_walkers) {
         int nW = std::min(pl->max_walkers, n_walkers - w0);
         size_t nb = (size_t)nW * pl->dev.D * sizeof(double);
-        memcpy(pl->h_params, params_host + (size_t)w0 * pl->dev.D, nb);
-        CUDA_TRY(cudaMemcpyAsync(pl->d_params, pl->h_params, nb, cudaMemcpyHostToDevice, st));
+        const double* src = params_host + (size_t)w0 * pl->dev.D;
+        if (!pin_in) { memcpy(pl->h_params, src, nb); src = pl->h_params; }
+        CUDA_TRY(cudaMemcpyAsync(pl->d_params, src, nb, cudaMemcpyHostToDevice, st));
         int rc = launch_walkers<0>(pl, full_mask(pl), pl->d_params, nW, pl->d_lnp, st, false);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(pl->h_lnp, pl->d_lnp, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+        double* dst = pin_out ? lnp_host + w0 : pl->h_lnp;
+        CUDA_TRY(cudaMemcpyAsync(dst, pl->d_lnp, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        memcpy(lnp_host + w0, pl->h_lnp, (size_t)nW * sizeof(double));
+        if (!pin_out) memcpy(lnp_host + w0, pl->h_lnp, (size_t)nW * sizeof(double));
     }
     return SPAMM_OK;
 }

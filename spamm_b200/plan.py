@@ -153,12 +153,16 @@ class ModelPlan(object):
         return out
 
     # -- host-buffer entry points ----------------------------------------------------
-    def lnposterior_host(self, params):
-        """numpy [W, D] -> numpy [W]; H2D / kernel / D2H inside the library."""
+    def lnposterior_host(self, params, out=None):
+        """numpy [W, D] -> numpy [W]; H2D / kernel / D2H inside the library.  Page-locked
+        buffers (e.g. views of torch pin_memory tensors) are used in place, pageable ones are
+        staged through the plan's pinned buffers."""
         p = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
         if p.shape[1] != self.n_dim:
             raise ValueError("expected %d parameters per walker, got %d" % (self.n_dim, p.shape[1]))
-        out = np.empty(p.shape[0], dtype=np.float64)
+        if out is None:
+            out = np.empty(p.shape[0], dtype=np.float64)
+        assert out.dtype == np.float64 and out.shape == (p.shape[0],) and out.flags.c_contiguous
         _lib.check(self.lib.spamm_lnpost_batch_host(self._h, p.ctypes.data_as(ctypes.c_void_p), p.shape[0],
                                                     out.ctypes.data_as(ctypes.c_void_p)))
         return out
