@@ -785,7 +785,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double w2 = sLine[gq * 12 + 4 + r4];
             double a = sLine[gq * 12 + 8 + r4];
             if (pl.line_type == SPAMM_LINE_LORENTZIAN) s += a / (d * d + w2);
-            else s += a * exp(-(d * d) / w2);
+            else s += a * exp_fast(-(d * d) / w2);
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) c.red[warp] = s;
@@ -942,7 +942,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
                         double d = lam[q] - lc;
-                        acc[q] = fma(rr, exp(-(d * d) / w2), acc[q]);                       // BC:319
+                        acc[q] = fma(rr, exp_fast(-(d * d) / w2), acc[q]);                       // BC:319
                     }
                 }
             }

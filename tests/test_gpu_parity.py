@@ -369,3 +369,37 @@ def test_non_canonical_component_order():
         f = m.model_flux_batch(params[:2])
         wantf = np.array([o.model_flux(p) for p in params[:2]])
         assert np.max(np.abs(f - wantf)) <= FLUX_RTOL * np.max(np.abs(wantf))
+
+
+def test_degenerate_data_values_follow_nan_to_num():
+    """Model.likelihood edge values (Model.py:440-443): a zero or NaN error / NaN flux pixel makes
+    the sum NaN -> 0.0; negative errors are squared away; an overflowing chi^2 -> -DBL_MAX."""
+    from oracle.spamm_numpy import OracleModel
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg2_nc_fe")
+    params = c.params[:12]
+    for kind in ("neg_err", "zero_err", "nan_flux", "huge_flux"):
+        d, e = c.flux.copy(), c.err.copy()
+        if kind == "neg_err":
+            e[::7] *= -1.0
+        elif kind == "zero_err":
+            e[100] = 0.0
+        elif kind == "nan_flux":
+            d[5] = np.nan
+        else:
+            d[7] = 1e160                       # ((d-m)/e)^2 overflows -> -inf -> -1.797e308
+        cc = Case.__new__(Case)
+        cc.wl, cc.flux, cc.err, cc.comps, cc.bc, cc.bpc = c.wl, d, e, c.comps, True, True
+        m = _model(cc)
+        m.components[0].norm_max, m.components[1].norm_max = float(c.hi[0]), float(c.hi[2])
+        m.invalidate_plan()
+        o = OracleModel(c.wl, d, e, comps=c.comps)
+        o.set_bounds(c.lo, c.hi)
+        with np.errstate(all="ignore"):
+            want = o.ln_posterior_batch(params)
+        got = m.lnposterior_batch(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL, (kind, got[:3], want[:3])
+        if kind in ("zero_err", "nan_flux"):
+            assert np.all(got[np.isfinite(want)] == 0.0)
+        if kind == "huge_flux":
+            assert np.all(got[np.isfinite(want)] == -1.7976931348623157e308)
