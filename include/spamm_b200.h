@@ -175,6 +175,13 @@ int spamm_plan_status(SpammPlan* plan, void* stream);
 /* number of kernels the library has launched on this plan since creation */
 int64_t spamm_plan_launch_count(const SpammPlan* plan);
 
+/* Small ensembles (emcee's default is 30 walkers, run_spamm.py:26): with fewer walkers than
+ * resident CTA slots the fused kernel runs one walker per thread-block CLUSTER and deals the
+ * walker's pixel tasks over the cluster's CTAs; the chi^2 partials are gathered through
+ * distributed shared memory in the same fixed order, so results do not depend on the split.
+ * mode 0: off; 1: automatic (default; 2/4/8 CTAs by ensemble size); 2, 4, 8: forced. */
+int spamm_plan_set_walker_split(SpammPlan* plan, int32_t mode);
+
 /* emcee 2.2.1 stretch move (EnsembleSampler._propose_stretch; call site
  * Model.py:283-289), one half-ensemble at a time, counter-based Philox RNG.
  *   propose: q[i] = c[r_i] - z_i (c[r_i] - s[i]),  z_i = ((a-1) u + 1)^2 / a

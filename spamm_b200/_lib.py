@@ -82,7 +82,7 @@ class SpammPlanDesc(ctypes.Structure):
 EXPORTS = [
     "spamm_plan_create", "spamm_plan_destroy", "spamm_lnpost_batch", "spamm_lnpost_batch_host", "spamm_lnpost_batch_p2p",
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
-    "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count",
+    "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split",
     "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record",
     "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version",
 ]
@@ -129,6 +129,8 @@ def load():
     lib.spamm_plan_status.restype = ctypes.c_int
     lib.spamm_plan_launch_count.argtypes = [vp]
     lib.spamm_plan_launch_count.restype = i64
+    lib.spamm_plan_set_walker_split.argtypes = [vp, i32]
+    lib.spamm_plan_set_walker_split.restype = ctypes.c_int
     lib.spamm_stretch_propose.argtypes = [vp, i32, i32, i32, dbl, u64, u64, vp, vp, vp]
     lib.spamm_stretch_propose.restype = ctypes.c_int
     lib.spamm_stretch_accept.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, u64, u64, vp, vp]

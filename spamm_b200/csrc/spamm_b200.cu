@@ -12,6 +12,7 @@
 //   NC / Fe / HG / BC   = spamm/components/{NuclearContinuumComponent,FeComponent,
 //                          HostGalaxyComponent,BalmerContinuumCombined}.py
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include <algorithm>
@@ -577,7 +578,10 @@ constexpr int kChunk = 32 * kPix;      // pixels per warp task
 // MODE 0: ln-posterior, 1: model flux out.  CANON: the live components are in the reference's
 // canonical order with the Balmer component last (run_spamm.py:100-122), so the model is
 // ((NC + Fe) + host) + Balmer and no per-component ordering state is carried through the task.
-template <int MODE, bool CANON>
+// SPLIT: small ensembles -- one walker per thread-block CLUSTER: every CTA of the cluster builds the
+// per-walker tables, the 64-pixel tasks are dealt round-robin over the CTAs, and CTA 0 gathers the
+// per-chunk chi^2 partials from its peers' shared memory (DSMEM) in the same fixed chunk order.
+template <int MODE, bool CANON, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
           uint32_t mask, DirectRows dr, PeerOut po) {
@@ -590,7 +594,13 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     double* sF0 = sChi + pl.n_chunks;                                           // [bc_nstage]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wloc = blockIdx.x;           // walker within this launch
+    int csize = 1, crank = 0;
+    if (SPLIT) {
+        cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+        csize = (int)cl.num_blocks();
+        crank = (int)cl.block_rank();
+    }
+    const int wloc = SPLIT ? blockIdx.x / csize : blockIdx.x;   // walker within this launch
     const int w = w0 + wloc;
     const int P = pl.P;
     const double* pw = params + (size_t)w * pl.D;
@@ -607,7 +617,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     __syncthreads();
     if (MODE == 0 && !c.prior_ok) {       // ln_posterior returns -inf before any flux (Model.py:67-69)
-        if (tid == 0) store_result(out, w, -CUDART_INF, po);
+        if (tid == 0 && crank == 0) store_result(out, w, -CUDART_INF, po);
         return;
     }
 
@@ -840,6 +850,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         int t = 0;
         if (lane == 0) t = atomicAdd(&c.next_task, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
+        if (SPLIT) t = t * csize + crank;                     // tasks dealt round-robin over the cluster
         if (t >= n_chunks) break;
         const int chunk = n_chunks - 1 - t;
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
@@ -976,15 +987,26 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // ---- per-walker reduction in fixed chunk order + likelihood (Model.py:440-445) ----------------
     if (MODE == 0) {
         __syncthreads();
-        if (warp == 0) {
+        if (SPLIT) cooperative_groups::this_cluster().sync();          // every CTA's partials are in place
+        if (warp == 0 && crank == 0) {
             double s = 0.0;
-            for (int k = lane; k < n_chunks; k += 32) s += sChi[k];
+            for (int k = lane; k < n_chunks; k += 32) {
+                if (SPLIT) {
+                    // chunk k was task t = n_chunks-1-k, handled by cluster rank t % csize
+                    const double* peer = cooperative_groups::this_cluster().map_shared_rank(
+                        sChi, (unsigned)((n_chunks - 1 - k) % csize));
+                    s += peer[k];
+                } else {
+                    s += sChi[k];
+                }
+            }
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) {
                 double ln_l = -0.5 * (s + pl.sum_ln);
                 store_result(out, w, nan_to_num(ln_l) + 0.0, po);      // + ln_prior (== 0 inside the box)
             }
         }
+        if (SPLIT) cooperative_groups::this_cluster().sync();          // peers' shared memory stays alive
     }
 }
 
@@ -1121,6 +1143,7 @@ struct SpammPlan {
     double *h_params = nullptr, *h_lnp = nullptr, *d_params = nullptr, *d_lnp = nullptr;
     cudaStream_t own_stream = nullptr;
     int max_sigma_seen = 0;
+    int split_mode = 1;          // 0: never split a walker over a cluster; 1: auto; 2/4/8: forced size
 };
 
 // Every device array gets kPad zeroed elements of slack: the fused kernel's last warp task
@@ -1503,10 +1526,15 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.n_chunks + pd.bc_nstage) * sizeof(double);
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+    const int sb = (int)pl->smem_bytes;
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
     CUDA_TRY(cudaDeviceSynchronize());
     return SPAMM_OK;
 }
@@ -1525,6 +1553,13 @@ extern "C" int spamm_plan_n_pix(const SpammPlan* pl) { return pl ? pl->dev.P : S
 extern "C" int spamm_plan_template_mode(const SpammPlan* pl) { return pl ? pl->template_mode : SPAMM_EINVAL; }
 extern "C" int spamm_plan_bank_rows(const SpammPlan* pl) { return pl ? pl->bank_rows : SPAMM_EINVAL; }
 extern "C" int64_t spamm_plan_launch_count(const SpammPlan* pl) { return pl ? pl->launches : 0; }
+extern "C" int spamm_plan_set_walker_split(SpammPlan* pl, int32_t mode) {
+    if (!pl) return set_error(SPAMM_EINVAL, "null plan");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8)
+        return set_error(SPAMM_EINVAL, "walker split must be 0 (off), 1 (auto), 2, 4 or 8");
+    pl->split_mode = mode;
+    return SPAMM_OK;
+}
 
 extern "C" int spamm_plan_status(SpammPlan* pl, void* stream) {
     if (!pl) return set_error(SPAMM_EINVAL, "null plan");
@@ -1589,6 +1624,49 @@ static bool canonical_order(const PlanDev& pd, uint32_t mask) {
     return true;
 }
 
+// One launch of the fused kernel.  Ensembles too small to fill the GPU (fewer walkers than
+// resident CTA slots) run one walker per thread-block cluster of 2/4/8 CTAs (SPLIT instantiation).
+template <int MODE, bool CANON, bool SPLIT>
+static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
+                      const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
+                      PeerOut po) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_walkers * csize), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = pl->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)csize;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    if (SPLIT) { cfg.attrs = &attr; cfg.numAttrs = 1; }
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT>, pd, params_dev, w0, out_dev, mask, dr, po));
+    return SPAMM_OK;
+}
+
+static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
+    if (pl->split_mode == 0) return 1;
+    int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
+    int c = 1;
+    while (c < 8 && n_walkers * c * 2 <= slots) c *= 2;
+    if (pl->split_mode > 1) c = pl->split_mode;          // forced (tests)
+    return c;
+}
+
+template <int MODE>
+static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, const PlanDev& pd,
+                    const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
+                    PeerOut po) {
+    const int c = cluster_size_for(pl, n_walkers);
+    if (c > 1) {
+        return canon ? launch_one<MODE, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po)
+                     : launch_one<MODE, false, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po);
+    }
+    return canon ? launch_one<MODE, true, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po)
+                 : launch_one<MODE, false, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+}
+
 template <int MODE>
 static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
                           double* out_dev, cudaStream_t st, bool force_direct,
@@ -1603,12 +1681,9 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
     bool direct = (need_fe || need_host) && (force_direct || pl->template_mode == SPAMM_TEMPLATES_DIRECT);
     if (!direct) {
         DirectRows dr{nullptr, nullptr, nullptr, nullptr};
-        if (canonical_order(pd, mask))
-            k_walkers<MODE, true><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
-        else
-            k_walkers<MODE, false><<<n_walkers, kThreads, pl->smem_bytes, st>>>(pd, params_dev, 0, out_dev, mask, dr, po);
+        int rc = launch_k<MODE>(pl, canonical_order(pd, mask), n_walkers, st, pd, params_dev, 0, out_dev, mask, dr, po);
+        if (rc) return rc;
         pl->launches += 1;
-        CUDA_TRY(cudaGetLastError());
         return SPAMM_OK;
     }
     int rc = ensure_direct_ws(pl);
@@ -1625,12 +1700,8 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
             dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
         }
         double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
-        if (canonical_order(pd, mask))
-            k_walkers<MODE, true><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
-        else
-            k_walkers<MODE, false><<<nW, kThreads, pl->smem_bytes, st>>>(pd, params_dev, w0, o, mask, dr, po);
+        if ((rc = launch_k<MODE>(pl, canonical_order(pd, mask), nW, st, pd, params_dev, w0, o, mask, dr, po))) return rc;
         pl->launches += 1;
-        CUDA_TRY(cudaGetLastError());
     }
     return SPAMM_OK;
 }

@@ -403,3 +403,38 @@ def test_degenerate_data_values_follow_nan_to_num():
             assert np.all(got[np.isfinite(want)] == 0.0)
         if kind == "huge_flux":
             assert np.all(got[np.isfinite(want)] == -1.7976931348623157e308)
+
+
+def test_walker_split_over_cluster_is_bit_identical():
+    """Small ensembles run one walker per thread-block cluster (2/4/8 CTAs share a walker's pixel
+    tasks, chi^2 partials gathered through distributed shared memory in the fixed chunk order):
+    every split must reproduce the one-CTA-per-walker result bit for bit, ln-posterior and flux,
+    including out-of-prior walkers and both the canonical and the generic component order."""
+    z, _ = lnpost_cases()
+    for name, comps in (("full_fp6", None), ("cfg1_nc_fp1", None), ("full_fp6", ["HOST", "BC", "PL", "FE"])):
+        c = Case(z, name)
+        if comps is None:
+            m = _model(c)
+            params = c.params[:30].copy()
+        else:
+            from oracle.spamm_numpy import OracleModel
+            o = OracleModel(c.wl, c.flux, c.err, comps=comps)
+            np.random.seed(5)
+            params = np.array([o.initial_values() for _ in range(30)])
+            cc = Case.__new__(Case)
+            cc.wl, cc.flux, cc.err, cc.comps, cc.bc, cc.bpc = c.wl, c.flux, c.err, comps, True, True
+            m = _model(cc)
+        params[3, -1] = 1e9                       # one walker outside its prior box -> -inf
+        m.plan.set_walker_split(0)
+        base = m.lnposterior_batch(params)
+        basef = m.model_flux_batch(params[:3])
+        assert np.isneginf(base[3]) and np.isfinite(base).sum() >= 20
+        if comps is None:
+            ok = np.isfinite(c.lnpost[:30])
+            ok[3] = False
+            assert rel_err(base[ok], c.lnpost[:30][ok]).max() < LNPOST_RTOL
+        for split in (2, 4, 8, 1):
+            m.plan.set_walker_split(split)
+            got = m.lnposterior_batch(params)
+            assert np.array_equal(got, base), (name, split, np.abs(got - base).max())
+            assert np.array_equal(m.model_flux_batch(params[:3]), basef), (name, split)
