@@ -439,8 +439,9 @@ __device__ int nearest_index_guess(const double* __restrict__ wl, int n, double 
 }
 
 // NuclearContinuumComponent.flux at pixel i (NC:176-201)
-__device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i, double hi, double lo) {
-    if (!pl.nc_broken) {
+__device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i, double hi, double lo,
+                                          bool broken) {
+    if (!broken) {
         // norm * (lam/lam0)^(-slope1)  (NC:195) as exp(-slope1 * ln x) with ln x (hi, lo) held in
         // double-double, so the result is within ~1 ulp of pow()
         double s = -c.nc_slope1;
@@ -470,8 +471,36 @@ __device__ __forceinline__ void templ_sum_n(const TemplCoef* __restrict__ tc, in
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         const double a = tc[j].a;
+        // one FMA per term (numpy rounds the product first: <= 0.5 ulp per term apart)
 #pragma unroll
-        for (int q = 0; q < kPix; ++q) out[q] = out[q] + a * v[j][q];                    // Fe:334 / HG:339
+        for (int q = 0; q < kPix; ++q) out[q] = fma(a, v[j][q], out[q]);                 // Fe:334 / HG:339
+    }
+}
+
+// two families with compile-time counts (FULL model): all NA + NB row loads in one batch
+template <int NA, int NB>
+__device__ __forceinline__ void templ_sum_2(const TemplCoef* __restrict__ tc, int i0, double (&outa)[kPix],
+                                            double (&outb)[kPix]) {
+    double v[NA + NB][kPix];
+#pragma unroll
+    for (int j = 0; j < NA + NB; ++j) {
+        const double* f = tc[j].f + i0;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) v[j][q] = f[q * 32];
+    }
+#pragma unroll
+    for (int q = 0; q < kPix; ++q) { outa[q] = 0.0; outb[q] = 0.0; }
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+        const double a = tc[j].a;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) outa[q] = fma(a, v[j][q], outa[q]);               // Fe:334
+    }
+#pragma unroll
+    for (int j = NA; j < NA + NB; ++j) {
+        const double a = tc[j].a;
+#pragma unroll
+        for (int q = 0; q < kPix; ++q) outb[q] = fma(a, v[j][q], outb[q]);               // HG:339
     }
 }
 
@@ -581,7 +610,11 @@ constexpr int kChunk = 32 * kPix;      // pixels per warp task
 // SPLIT: small ensembles -- one walker per thread-block CLUSTER: every CTA of the cluster builds the
 // per-walker tables, the 64-pixel tasks are dealt round-robin over the CTAs, and CTA 0 gathers the
 // per-chunk chi^2 partials from its peers' shared memory (DSMEM) in the same fixed chunk order.
-template <int MODE, bool CANON, bool SPLIT>
+// FULL: compile-time view of the headline model (run_spamm's NC + Fe x3 + host x7 + BalmerCombined with
+// both parts on, Lorentzian lines, far-field series, bank rows): every component test, template count
+// and line-type branch below folds away, which roughly halves the non-FP64 instructions of a task.
+constexpr int kFullFe = 3, kFullHost = 7;
+template <int MODE, bool CANON, bool SPLIT, bool FULL>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
           uint32_t mask, DirectRows dr, PeerOut po) {
@@ -632,10 +665,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         else if (kind == SPAMM_COMP_HOST) has_host = true;
         else if (kind == SPAMM_COMP_BALMER) { off_bal = pl.comp_off[q]; q_bal = q; }
     }
-    const bool have_balmer = off_bal >= 0;
-    const int n_fe = has_fe ? pl.fe.n_templ : 0, n_host = has_host ? pl.host.n_templ : 0;
-    const bool do_bc = have_balmer && pl.bc_on;
-    const bool do_bpc = have_balmer && pl.bpc_on;
+    if (FULL) { has_fe = true; has_host = true; }
+    const bool has_nc = FULL ? true : off_nc >= 0;
+    const bool nc_broken = FULL ? false : pl.nc_broken != 0;
+    const bool have_balmer = FULL ? true : off_bal >= 0;
+    const int n_fe = FULL ? kFullFe : (has_fe ? pl.fe.n_templ : 0);
+    const int n_host = FULL ? kFullHost : (has_host ? pl.host.n_templ : 0);
+    const bool do_bc = FULL ? true : have_balmer && pl.bc_on;
+    const bool do_bpc = FULL ? true : have_balmer && pl.bpc_on;
+    const bool lorentz = FULL ? true : pl.line_type == SPAMM_LINE_LORENTZIAN;
+    const bool series_on = FULL ? true : pl.series_on != 0;
+    const bool fe_rows_direct = FULL ? false : dr.fe_f != nullptr;
+    const bool host_rows_direct = FULL ? false : dr.host_f != nullptr;
 
     double b_norm = 0, b_Te = 0, b_tau = 0, b_loff = 0, b_lwid = 0, b_logNe = 0;
     if (have_balmer) {
@@ -646,8 +687,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const double kT = pl.kb * b_Te;                      // k.value*T, BC:296
 
     // ---- P1: independent per-walker scalars, spread over the warps ------------------------
-    if (tid == 0 && off_nc >= 0) {
-        if (!pl.nc_broken) {
+    if (tid == 0 && has_nc) {
+        if (!nc_broken) {
             c.nc_norm = c.p[off_nc]; c.nc_slope1 = c.p[off_nc + 1];
             c.nc_slope2 = 0; c.nc_break = 0;
         } else {
@@ -655,12 +696,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             c.nc_slope1 = c.p[off_nc + 2]; c.nc_slope2 = c.p[off_nc + 3];
         }
     }
-    if (has_fe && warp == 1 && lane < pl.fe.n_templ) {
+    if (has_fe && warp == 1 && lane < n_fe) {
         const TemplDev& ts = pl.fe;
         int t = lane;
         double norm = c.p[ts.param_off + t];
         const double* f; double nf;
-        if (dr.fe_f != nullptr) {
+        if (fe_rows_direct) {
             size_t row = (size_t)wloc * ts.n_templ + t;
             f = dr.fe_f + row * P; nf = dr.fe_nf[row];
         } else {
@@ -674,12 +715,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         c.tc[t].f = f;
         c.tc[t].a = norm / nf;                                          // Fe:334
     }
-    if (has_host && warp == 2 && lane < pl.host.n_templ) {
+    if (has_host && warp == 2 && lane < n_host) {
         const TemplDev& ts = pl.host;
         int t = lane;
         double norm = c.p[ts.param_off + t];
         const double* f; double nf;
-        if (dr.host_f != nullptr) {
+        if (host_rows_direct) {
             size_t row = (size_t)wloc * ts.n_templ + t;
             f = dr.host_f + row * P; nf = dr.host_nf[row];
         } else {
@@ -770,7 +811,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double wv = sW[n], rr = sG[n];
             if (n < n_lines) {
                 sLine[gq * 12 + 4 + r4] = wv * wv;
-                sLine[gq * 12 + 8 + r4] = (pl.line_type == SPAMM_LINE_LORENTZIAN) ? rr * wv : rr;
+                sLine[gq * 12 + 8 + r4] = lorentz ? rr * wv : rr;
             } else {   // padding: contributes exactly 0
                 sLine[gq * 12 + 4 + r4] = 1.0;
                 sLine[gq * 12 + 8 + r4] = 0.0;
@@ -794,14 +835,13 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double d = lam - sLine[gq * 12 + r4];
             double w2 = sLine[gq * 12 + 4 + r4];
             double a = sLine[gq * 12 + 8 + r4];
-            if (pl.line_type == SPAMM_LINE_LORENTZIAN) s += a / (d * d + w2);
+            if (lorentz) s += a / (d * d + w2);
             else s += a * exp_fast(-(d * d) / w2);
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) c.red[warp] = s;
         // cluster moments M_k = sum_n a_n d_n^k and per-walker cluster constants: one warp each
-        const int n_cl = pl.series_on && pl.line_type == SPAMM_LINE_LORENTZIAN
-                             ? pl.n_clusters + pl.n_super : 0;
+        const int n_cl = series_on && lorentz ? pl.n_clusters + pl.n_super : 0;
         if (warp < n_cl) {
             const ClusterDev& cd = pl.cl[warp];
             const double* dd = pl.line_d[warp];
@@ -863,25 +903,29 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         for (int q = 0; q < kPix; ++q) {
             acc[q] = 0.0;
             post[q] = 0.0;
-            lnhi[q] = off_nc >= 0 ? pl.nc_lnx_hi[i0 + 32 * q] : 0.0;
-            lnlo[q] = off_nc >= 0 ? pl.nc_lnx_lo[i0 + 32 * q] : 0.0;
+            lnhi[q] = has_nc ? pl.nc_lnx_hi[i0 + 32 * q] : 0.0;
+            lnlo[q] = has_nc ? pl.nc_lnx_lo[i0 + 32 * q] : 0.0;
             lam[q] = pl.wl[i0 + 32 * q];
             dat[q] = MODE == 0 ? pl.flux[i0 + 32 * q] : 0.0;
             ierr[q] = MODE == 0 ? pl.inv_err[i0 + 32 * q] : 0.0;
         }
         {
             double fe_v[kPix], host_v[kPix], nc_v[kPix];
-            if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
-            if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
+            if (FULL) {
+                templ_sum_2<kFullFe, kFullHost>(c.tc, i0, fe_v, host_v);
+            } else {
+                if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
+                if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
+            }
 #pragma unroll
             for (int q = 0; q < kPix; ++q)
-                nc_v[q] = off_nc >= 0 ? nc_flux(pl, c, i0 + 32 * q, lnhi[q], lnlo[q]) : 0.0;
+                nc_v[q] = has_nc ? nc_flux(pl, c, i0 + 32 * q, lnhi[q], lnlo[q], nc_broken) : 0.0;
             if (CANON) {
                 // model_spectrum.flux starts at zero and adds NC, Fe, host in turn (Model.py:350-380)
 #pragma unroll
                 for (int q = 0; q < kPix; ++q) {
                     double v = 0.0;
-                    if (off_nc >= 0) v = v + nc_v[q];
+                    if (has_nc) v = v + nc_v[q];
                     if (n_fe) v = v + fe_v[q];
                     if (n_host) v = v + host_v[q];
                     m[q] = v;
@@ -904,7 +948,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
         }
         if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
-            if (pl.line_type == SPAMM_LINE_LORENTZIAN) {
+            if (lorentz) {
                 // The line sum is a short list of segments, each either a run of line groups summed
                 // directly or one cluster summed by its far-field series (one instance of each body):
                 //   exact mode            : [direct 0..n_groups)
@@ -912,7 +956,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 //   otherwise             : [direct 0..g_direct_end) then per base cluster series|direct
                 int sup = -1, nseg = 1;
                 double sup_cmin = 0.0;
-                if (pl.series_on) {
+                if (series_on) {
                     // nested supersets {n >= n_k}, widest first: the first one that is far from every
                     // pixel of the task absorbs all its lines
                     const double lam_first = pl.wl[chunk * kChunk];     // uniform: the nearest pixel when
@@ -930,7 +974,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                     int g0 = 0, g1 = n_groups, kc = 0;
                     double cmin = 0.0;
                     bool series = false;
-                    if (pl.series_on) {
+                    if (series_on) {
                         if (sg == 0) {
                             g1 = sup >= 0 ? pl.cl[sup].g_lo : pl.g_direct_end;
                         } else if (sup >= 0) {
@@ -1144,6 +1188,7 @@ struct SpammPlan {
     cudaStream_t own_stream = nullptr;
     int max_sigma_seen = 0;
     int split_mode = 1;          // 0: never split a walker over a cluster; 1: auto; 2/4/8: forced size
+    bool use_full_kernel = getenv("SPAMM_NO_FULL_KERNEL") == nullptr;   // tests compare it with the generic one
 };
 
 // Every device array gets kPad zeroed elements of slack: the fused kernel's last warp task
@@ -1527,14 +1572,16 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
     const int sb = (int)pl->smem_bytes;
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
     CUDA_TRY(cudaDeviceSynchronize());
     return SPAMM_OK;
 }
@@ -1626,7 +1673,7 @@ static bool canonical_order(const PlanDev& pd, uint32_t mask) {
 
 // One launch of the fused kernel.  Ensembles too small to fill the GPU (fewer walkers than
 // resident CTA slots) run one walker per thread-block cluster of 2/4/8 CTAs (SPLIT instantiation).
-template <int MODE, bool CANON, bool SPLIT>
+template <int MODE, bool CANON, bool SPLIT, bool FULL = false>
 static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
                       const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                       PeerOut po) {
@@ -1641,7 +1688,7 @@ static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, 
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     if (SPLIT) { cfg.attrs = &attr; cfg.numAttrs = 1; }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT>, pd, params_dev, w0, out_dev, mask, dr, po));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, FULL>, pd, params_dev, w0, out_dev, mask, dr, po));
     return SPAMM_OK;
 }
 
@@ -1654,11 +1701,24 @@ static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
     return c;
 }
 
+// the headline model the FULL instantiation is compiled for
+static bool full_model(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, const DirectRows& dr) {
+    if (!pl->use_full_kernel || pd.n_comp != 4 || mask != 0xFu || dr.fe_f || dr.host_f) return false;
+    return pd.comp_kind[0] == SPAMM_COMP_NUCLEAR && pd.comp_kind[1] == SPAMM_COMP_FE &&
+           pd.comp_kind[2] == SPAMM_COMP_HOST && pd.comp_kind[3] == SPAMM_COMP_BALMER && !pd.nc_broken &&
+           pd.fe.n_templ == kFullFe && pd.host.n_templ == kFullHost && pd.bc_on && pd.bpc_on &&
+           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on;
+}
+
 template <int MODE>
 static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, const PlanDev& pd,
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                     PeerOut po) {
     const int c = cluster_size_for(pl, n_walkers);
+    if (MODE == 0 && full_model(pl, pd, mask, dr)) {
+        if (c > 1) return launch_one<0, true, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        return launch_one<0, true, false, true>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+    }
     if (c > 1) {
         return canon ? launch_one<MODE, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po)
                      : launch_one<MODE, false, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po);

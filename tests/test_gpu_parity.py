@@ -438,3 +438,22 @@ def test_walker_split_over_cluster_is_bit_identical():
             got = m.lnposterior_batch(params)
             assert np.array_equal(got, base), (name, split, np.abs(got - base).max())
             assert np.array_equal(m.model_flux_batch(params[:3]), basef), (name, split)
+
+
+def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
+    """The headline model (NC + Fe x3 + host x7 + Balmer, Lorentzian, bank rows) runs a compile-time
+    specialised instantiation of the fused kernel; it performs the same operations in the same order
+    as the generic instantiation, so the two must agree bit for bit (and with the fixture)."""
+    z, _ = lnpost_cases()
+    c = Case(z, "cfg5_full")
+    m_full = _model(c)
+    got = m_full.lnposterior_batch(c.params)
+    monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+    m_gen = _model(c)
+    ref = m_gen.lnposterior_batch(c.params)
+    monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
+    assert np.array_equal(got, ref)
+    assert rel_err(got, c.lnpost).max() < LNPOST_RTOL
+    for split in (2, 8):
+        m_full.plan.set_walker_split(split)
+        assert np.array_equal(m_full.lnposterior_batch(c.params), ref)
