@@ -122,6 +122,7 @@ struct PlanDev {
     int bc_nstage;
     double bc_dlnew;
     double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
+    int exp_safe;                         // the prior box bounds every exp() argument of the fused kernel
     int* status;
 };
 
@@ -199,8 +200,9 @@ __constant__ double kExpPoly[10] = {
     0.00019841269589115497, 0.001388888894591638, 0.008333333333455043, 0.041666666666519754,
     0.16666666666666477, 0.5000000000000012};
 
+template <bool CHECK = true>
 __device__ __forceinline__ double exp_fast(double x) {
-    if (!(fabs(x) < 700.0)) return exp(x);
+    if (CHECK && !(fabs(x) < 700.0)) return exp(x);
     const double magic = 6755399441055744.0;
     double t = fma(x, 1.4426950408889634, magic);
     int ki = __double2loint(t);
@@ -381,13 +383,17 @@ __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) 
 
 // unnormalised Balmer continuum sample (1 - exp(-tau)) * blackbody_lambda (BC:435-440).
 // bc_K[k] = 2 h nu^3 c_AA / (c_cgs^2 lambda^2) is the walker-independent factor of B_lambda.
-__device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double tauBE) {
-    double log_boltz = pl.bc_hnu[k] / kT;
+// SAFE (FULL kernel: the prior box bounds every exp argument, PlanDev::exp_safe): no range checks,
+// and the two divisions become a multiplication by 1/kT (<= 1.5 ulp on the exponent, i.e. <= 1e-15
+// relative at T >= 5000 K) and a 1-ulp reciprocal.
+template <bool SAFE>
+__device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double inv_kT, double tauBE) {
+    double log_boltz = SAFE ? pl.bc_hnu[k] * inv_kT : pl.bc_hnu[k] / kT;
     // expm1(x): for x >= 0.5 (T < 8e4 K at 3646 A) exp(x) - 1 loses at most one bit
-    double boltzm1 = log_boltz >= 0.5 ? exp_fast(log_boltz) - 1.0 : expm1(log_boltz);
-    double flam = pl.bc_K[k] / boltzm1;
+    double boltzm1 = log_boltz >= 0.5 ? exp_fast<!SAFE>(log_boltz) - 1.0 : expm1(log_boltz);
+    double flam = SAFE ? pl.bc_K[k] * rcp_fast(boltzm1) : pl.bc_K[k] / boltzm1;
     double tau = tauBE * pl.bc_t3[k];
-    double absorption = 1 - exp_fast(-tau);
+    double absorption = 1 - exp_fast<!SAFE>(-tau);
     return absorption * flam;
 }
 
@@ -439,6 +445,7 @@ __device__ int nearest_index_guess(const double* __restrict__ wl, int n, double 
 }
 
 // NuclearContinuumComponent.flux at pixel i (NC:176-201)
+template <bool SAFE>
 __device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c, int i, double hi, double lo,
                                           bool broken) {
     if (!broken) {
@@ -447,7 +454,7 @@ __device__ __forceinline__ double nc_flux(const PlanDev& pl, const WalkerCtx& c,
         double s = -c.nc_slope1;
         double th = s * hi;
         double tl = fma(s, hi, -th) + s * lo;
-        double v = exp_fast(th);
+        double v = exp_fast<!SAFE>(th);
         v = fma(v, tl, v);
         return c.nc_norm * v;
     }
@@ -563,32 +570,31 @@ __device__ __forceinline__ double cluster_cmin(const ClusterW& cw, const double 
 //   with q(delta) = As (delta/R)^2 - 2R(u - kappa c_bar)(delta/R) + C
 __device__ __forceinline__ void cluster_series(const ClusterW& cw, int K, const double (&lam)[kPix],
                                                double (&acc)[kPix]) {
-    double t1[kPix], t2[kPix], al[kPix], be[kPix], sum[kPix];
-    const double m0 = cw.mom[0], m1 = cw.mom[1];
+    // Clenshaw summation of sum_k M_k t_k for t_k = beta t_{k-1} + alpha t_{k-2}, t_0 = 1/C, t_1 = beta t_0:
+    //   b_k = M_k + beta b_{k+1} + alpha b_{k+2},  sum = t_0 b_0     (2 FMA per term and pixel)
+    double al[kPix], be[kPix], invC[kPix], bh[kPix], bl[kPix];
+    const double mh = cw.mom[K - 1], ml = cw.mom[K - 2];
 #pragma unroll
     for (int q = 0; q < kPix; ++q) {
         double u = lam[q] - cw.cb;
-        double invC = rcp_fast(fma(u, u, cw.kcb2));
-        be[q] = fma(u, cw.twoR, -cw.twoRkcb) * invC;
-        al[q] = cw.negAs * invC;
-        t2[q] = invC;
-        t1[q] = be[q] * invC;
-        sum[q] = fma(t1[q], m1, invC * m0);
+        invC[q] = rcp_fast(fma(u, u, cw.kcb2));
+        be[q] = fma(u, cw.twoR, -cw.twoRkcb) * invC[q];
+        al[q] = cw.negAs * invC[q];
+        bh[q] = mh;                                   // b_{K-1}
+        bl[q] = fma(be[q], mh, ml);                   // b_{K-2}
     }
-    // two terms per trip (K is made even by series_terms): t2 <- t(k), t1 <- t(k+1)
+    // two terms per trip (K is even): bh <- b_k, bl <- b_{k-1}
 #pragma unroll 1
-    for (int k = 2; k < K; k += 2) {
-        const double mk = cw.mom[k], mk1 = cw.mom[k + 1];
+    for (int k = K - 3; k > 0; k -= 2) {
+        const double mk = cw.mom[k], mk1 = cw.mom[k - 1];
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
-            t2[q] = fma(be[q], t1[q], al[q] * t2[q]);
-            sum[q] = fma(t2[q], mk, sum[q]);
-            t1[q] = fma(be[q], t2[q], al[q] * t1[q]);
-            sum[q] = fma(t1[q], mk1, sum[q]);
+            bh[q] = fma(be[q], bl[q], fma(al[q], bh[q], mk));
+            bl[q] = fma(be[q], bh[q], fma(al[q], bl[q], mk1));
         }
     }
 #pragma unroll
-    for (int q = 0; q < kPix; ++q) acc[q] += sum[q];
+    for (int q = 0; q < kPix; ++q) acc[q] = fma(invC[q], bl[q], acc[q]);
 }
 
 // number of series terms for rho^2 = As / Cmin  (rho^K <~ 1e-16; capped at kMom, which the
@@ -800,7 +806,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     if (do_bc && tid >= 32) {
         const double tauBE = b_tau;
         int nst = min(pl.bc_nstage, P);
-        for (int k = tid - 32; k < nst; k += kThreads - 32) sF0[k] = bc_f0(pl, k, kT, tauBE);
+        const double inv_kT = 1.0 / kT;
+        for (int k = tid - 32; k < nst; k += kThreads - 32) sF0[k] = bc_f0<FULL>(pl, k, kT, inv_kT, tauBE);
     }
     __syncthreads();
 
@@ -886,9 +893,11 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const int n_chunks = pl.n_chunks;
     const int n_groups = n_pad >> 2;
     const double2* sL2 = reinterpret_cast<const double2*>(sLine);
+    const uint32_t next_task_addr = (uint32_t)__cvta_generic_to_shared(&c.next_task);
     for (;;) {
         int t = 0;
-        if (lane == 0) t = atomicAdd(&c.next_task, 1);
+        if (lane == 0)      // plain atom.shared: the compiler's atomicAdd expands to a warp-aggregation sequence
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(next_task_addr) : "memory");
         t = __shfl_sync(0xffffffffu, t, 0);
         if (SPLIT) t = t * csize + crank;                     // tasks dealt round-robin over the cluster
         if (t >= n_chunks) break;
@@ -919,7 +928,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
 #pragma unroll
             for (int q = 0; q < kPix; ++q)
-                nc_v[q] = has_nc ? nc_flux(pl, c, i0 + 32 * q, lnhi[q], lnlo[q], nc_broken) : 0.0;
+                nc_v[q] = has_nc ? nc_flux<FULL>(pl, c, i0 + 32 * q, lnhi[q], lnlo[q], nc_broken) : 0.0;
             if (CANON) {
                 // model_spectrum.flux starts at zero and adds NC, Fe, host in turn (Model.py:350-380)
 #pragma unroll
@@ -1567,6 +1576,30 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         pd.edge_guess = (int)(std::lower_bound(d->wl, d->wl + P, d->balmer_edge) - d->wl);
     }
 
+    // exp_safe: inside the prior box every exp() argument of the fused kernel stays below 690 in
+    // magnitude, so the FULL instantiation (ln-posterior only: out-of-prior walkers exit first) can
+    // drop the range checks.  NC: |slope| max|ln(wl/wl0)|; BC: h nu / (k Te) at the bluest pixel and
+    // Te_min; tau_BE (wl/edge)^3 over the staged pixels.
+    pd.exp_safe = 0;
+    if (d->prior_lo && d->prior_hi && seen[SPAMM_COMP_NUCLEAR] && seen[SPAMM_COMP_BALMER] && !d->nc_broken_pl &&
+        pd.bc_on) {
+        int o_nc = -1, o_bal = -1;
+        for (int q = 0; q < pd.n_comp; ++q) {
+            if (pd.comp_kind[q] == SPAMM_COMP_NUCLEAR) o_nc = pd.comp_off[q];
+            if (pd.comp_kind[q] == SPAMM_COMP_BALMER) o_bal = pd.comp_off[q];
+        }
+        double lmax = 0.0;
+        for (int i = 0; i < P; ++i) lmax = std::max(lmax, std::fabs(std::log(d->wl[i] / d->nc_norm_wl)));
+        const double smax = std::max(std::fabs(d->prior_lo[o_nc + 1]), std::fabs(d->prior_hi[o_nc + 1]));
+        const double te_lo = d->prior_lo[o_bal + 1];
+        const double taumax = std::max(std::fabs(d->prior_lo[o_bal + 2]), std::fabs(d->prior_hi[o_bal + 2]));
+        const double hnu0 = d->h_cgs * (d->c_aa / d->wl[0]);
+        const double t3max = std::pow(d->wl[std::max(pd.bc_nstage, 1) - 1] / d->balmer_edge, 3.0);
+        const bool ok = smax * lmax < 690.0 && te_lo > 0.0 && hnu0 / (d->kb_cgs * te_lo) < 690.0 &&
+                        taumax * t3max < 690.0;
+        pd.exp_safe = ok ? 1 : 0;    // NaN bounds compare false
+    }
+
     // shared memory of the fused kernel
     pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.n_chunks + pd.bc_nstage) * sizeof(double);
     if (pl->smem_bytes > 200 * 1024)
@@ -1707,7 +1740,7 @@ static bool full_model(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, co
     return pd.comp_kind[0] == SPAMM_COMP_NUCLEAR && pd.comp_kind[1] == SPAMM_COMP_FE &&
            pd.comp_kind[2] == SPAMM_COMP_HOST && pd.comp_kind[3] == SPAMM_COMP_BALMER && !pd.nc_broken &&
            pd.fe.n_templ == kFullFe && pd.host.n_templ == kFullHost && pd.bc_on && pd.bpc_on &&
-           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on;
+           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on && pd.exp_safe && pd.lo != nullptr;
 }
 
 template <int MODE>

@@ -441,9 +441,10 @@ def test_walker_split_over_cluster_is_bit_identical():
 
 
 def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
-    """The headline model (NC + Fe x3 + host x7 + Balmer, Lorentzian, bank rows) runs a compile-time
-    specialised instantiation of the fused kernel; it performs the same operations in the same order
-    as the generic instantiation, so the two must agree bit for bit (and with the fixture)."""
+    """The headline model (NC + Fe x3 + host x7 + Balmer, Lorentzian, bank rows, prior box that bounds
+    every exp argument) runs a compile-time specialised instantiation of the fused kernel without exp
+    range checks and with reciprocal-multiplies in the blackbody; it must agree with the generic
+    instantiation to a few ulp (and with the fixture), and be independent of the cluster split."""
     z, _ = lnpost_cases()
     c = Case(z, "cfg5_full")
     m_full = _model(c)
@@ -452,8 +453,9 @@ def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
     m_gen = _model(c)
     ref = m_gen.lnposterior_batch(c.params)
     monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
-    assert np.array_equal(got, ref)
+    assert rel_err(got, ref).max() < 1e-13
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
     assert rel_err(got, c.lnpost).max() < LNPOST_RTOL
     for split in (2, 8):
         m_full.plan.set_walker_split(split)
-        assert np.array_equal(m_full.lnposterior_batch(c.params), ref)
+        assert np.array_equal(m_full.lnposterior_batch(c.params), got)
