@@ -410,7 +410,8 @@ __device__ __forceinline__ double bc_conv_at(const PlanDev& pl, const double* __
 }
 
 struct alignas(16) ClusterW {    // per-walker constants of one cluster
-    double cb, kcb2, twoR, twoRkcb, negAs, thr, As, pad;
+    double cb, kcb2, twoR, twoRkcb, negAs, thr, As;
+    double far_lam;     // tasks whose first pixel is at or beyond this wavelength are far (rho <= 0.1)
     double mom[kMom];
 };
 
@@ -425,6 +426,7 @@ struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     int bc_istar, bpc_istar;
     int prior_ok;
     int next_task;
+    int bc_finite;       // bc_scale is finite: chunks without Balmer-continuum pixels may skip the 0 * scale
 };
 static_assert(sizeof(WalkerCtx) % 16 == 0, "line table must stay 16-byte aligned");
 
@@ -764,7 +766,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     if (do_bpc) {
         const double shift = b_loff / pl.c_kms;          // BC:379
         const double width = b_lwid / pl.c_kms;
-        const double n_e = pow(10.0, b_logNe);           // BC:376
+        // BC:376; only the SH95 look-ups (n <= 50, the first threads) use it
+        const double n_e = pl.line_min + tid <= 50 ? pow(10.0, b_logNe) : 0.0;
         for (int n = tid; n < n_pad; n += kThreads) {
             double lc = 0.0, wv = 0.0, rg = 0.0;
             if (n < n_lines) {
@@ -828,6 +831,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     if (do_bc && warp == 7 && lane == 0) {
         double fnorm = bc_conv_at(pl, sF0, c.bc_istar);                  // BC:444
         c.bc_scale = b_norm / fnorm;                                     // BC:446
+        c.bc_finite = isfinite(c.bc_scale) ? 1 : 0;
     }
     __syncthreads();
 
@@ -861,12 +865,21 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
 #pragma unroll
                 for (int k = 0; k < kMom; ++k) { mk[k] += pw; pw *= dn; }
             }
+            // lane sums of all 16 moments by a halving butterfly (16 shuffled doubles instead of 80;
+            // same xor tree 16, 8, 4, 2, 1 per moment): lane 2k ends up with moment k
+            static_assert(kMom == 16, "butterfly below is written for 16 moments");
 #pragma unroll
-            for (int k = 0; k < kMom; ++k) {
-                double v = mk[k];
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) c.cw[warp].mom[k] = v;
+            for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+                const bool up = (lane & bit) != 0;
+#pragma unroll
+                for (int k = 0; k < h; ++k) {
+                    const double send = up ? mk[k] : mk[k + h];
+                    const double keep = up ? mk[k + h] : mk[k];
+                    mk[k] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+                }
             }
+            mk[0] += __shfl_xor_sync(0xffffffffu, mk[0], 1);
+            if (!(lane & 1)) c.cw[warp].mom[lane >> 1] = mk[0];
             if (lane == 0) {
                 const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
                 const double kappa = width * width;
@@ -879,6 +892,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 cw.As = (1.0 + kappa) * R * R;
                 cw.negAs = -cw.As;
                 cw.thr = 100.0 * cw.As;                              // rho <= 0.1
+                // redward of c_bar the nearest pixel of a task is its first one: u^2 + kcb2 >= thr
+                cw.far_lam = cb + sqrt(fmax(cw.thr - cw.kcb2, 0.0)) * (1.0 + 1e-12);
             }
         }
         __syncthreads();
@@ -887,6 +902,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         bpc_scale = b_norm / tot;                                        // BC:387
     }
     const double bc_scale = c.bc_scale;
+    const bool bc_finite = c.bc_finite != 0;
     double* fout = (MODE == 1) ? out + (size_t)wloc * P : nullptr;
 
     // ---- main phase: each warp pulls 64-pixel tasks, reddest (line-heavy) chunks first ------------
@@ -956,7 +972,11 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 }
             }
         }
-        if (do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar) {
+        // warp-uniform: does this task hold any Balmer-continuum / pseudo-continuum pixel?  (a non-finite
+        // scale keeps the reference's 0 * scale = NaN on every pixel, BC:445-446)
+        const bool task_bc = do_bc && (chunk * kChunk <= bc_istar || !bc_finite);
+        const bool task_bpc = do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar;
+        if (task_bpc) {
             if (lorentz) {
                 // The line sum is a short list of segments, each either a run of line groups summed
                 // directly or one cluster summed by its far-field series (one instance of each body):
@@ -968,13 +988,14 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 if (series_on) {
                     // nested supersets {n >= n_k}, widest first: the first one that is far from every
                     // pixel of the task absorbs all its lines
-                    const double lam_first = pl.wl[chunk * kChunk];     // uniform: the nearest pixel when
-                    for (int sidx = 0; sidx < pl.n_super && sup < 0; ++sidx) {   // the task is redward of c_bar
-                        const ClusterW& cw = c.cw[pl.n_clusters + sidx];
-                        double cmin;
-                        if (lam_first >= cw.cb) { double u = lam_first - cw.cb; cmin = fma(u, u, cw.kcb2); }
-                        else cmin = cluster_cmin(cw, lam);
-                        if (cmin >= cw.thr) { sup = pl.n_clusters + sidx; sup_cmin = cmin; }
+                    // (lane 0 holds the task's first pixel, the nearest one when the task is redward of c_bar)
+                    const double lam_first = __shfl_sync(0xffffffffu, lam[0], 0);
+                    for (int sidx = 0; sidx < pl.n_super; ++sidx) {
+                        if (lam_first >= c.cw[pl.n_clusters + sidx].far_lam) { sup = pl.n_clusters + sidx; break; }
+                    }
+                    if (sup >= 0) {
+                        const double u = lam_first - c.cw[sup].cb;
+                        sup_cmin = fma(u, u, c.cw[sup].kcb2);
                     }
                     nseg = sup >= 0 ? 2 : 1 + pl.n_clusters;
                 }
@@ -1018,7 +1039,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double v = m[q];
             if (have_balmer) {
                 double bc = 0.0, bpc = 0.0;
-                if (do_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale;   // BC:445-446
+                if (task_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale; // BC:445-446
                 if (do_bpc) bpc = ((i > bpc_istar) ? acc[q] : 0.0) * bpc_scale;                // BC:386-387
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
