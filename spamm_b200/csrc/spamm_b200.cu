@@ -107,6 +107,7 @@ struct PlanDev {
     // Balmer
     int bc_on, bpc_on, line_type, line_min, n_lines, n_lines_pad;
     const double *line_c0, *line_e;
+    const double* line_cum;               // n > 50: sum_{m=51..n} line_e[m] (the ratio recursion telescoped)
     double sh_ne[SPAMM_SH95_NE], sh_T[SPAMM_SH95_T];
     const double* sh_z;
     // far-field clusters of the line forest (see DESIGN.md "line-sum"): contiguous groups of
@@ -387,12 +388,12 @@ __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) 
 // and the two divisions become a multiplication by 1/kT (<= 1.5 ulp on the exponent, i.e. <= 1e-15
 // relative at T >= 5000 K) and a 1-ulp reciprocal.
 template <bool SAFE>
-__device__ __forceinline__ double bc_f0(const PlanDev& pl, int k, double kT, double inv_kT, double tauBE) {
-    double log_boltz = SAFE ? pl.bc_hnu[k] * inv_kT : pl.bc_hnu[k] / kT;
+__device__ __forceinline__ double bc_f0(double hnu, double K, double t3, double kT, double inv_kT, double tauBE) {
+    double log_boltz = SAFE ? hnu * inv_kT : hnu / kT;
     // expm1(x): for x >= 0.5 (T < 8e4 K at 3646 A) exp(x) - 1 loses at most one bit
     double boltzm1 = log_boltz >= 0.5 ? exp_fast<!SAFE>(log_boltz) - 1.0 : expm1(log_boltz);
-    double flam = SAFE ? pl.bc_K[k] * rcp_fast(boltzm1) : pl.bc_K[k] / boltzm1;
-    double tau = tauBE * pl.bc_t3[k];
+    double flam = SAFE ? K * rcp_fast(boltzm1) : K / boltzm1;
+    double tau = tauBE * t3;
     double absorption = 1 - exp_fast<!SAFE>(-tau);
     return absorption * flam;
 }
@@ -776,49 +777,44 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 wv = width * lc;                         // BC:316
                 int nn = pl.line_min + n;
                 if (nn <= 50) rg = sh95_bilinear(pl, 50 - nn, n_e, b_Te);   // coef_use[-i+2], BC:294
-                else rg = exp(pl.line_e[n] / kT);                            // BC:296
+                else rg = exp(pl.line_cum[n] / kT);                          // BC:296, telescoped
             }
             sLine[(n >> 2) * 12 + (n & 3)] = lc;
             sW[n] = wv;
-            sG[n] = rg;      // ratio (n <= 50) or the recursion factor (n > 50)
+            sG[n] = rg;      // ratio (n <= 50) or r_n / r_50 (n > 50)
         }
     }
-    __syncthreads();
-
-    // ---- P2: ratio recursion flux_ratios[i] = flux_ratios[i-1] * exp(...) for n > 50 (BC:292-296)
-    // as a warp-parallel prefix product: each lane multiplies its contiguous segment, an exclusive
-    // multiplicative scan over the 32 segment totals supplies the carry (same factors as the
-    // sequential loop, re-associated: a few ulp)
-    if (warp == 0 && do_bpc) {
-        const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
-        const int cnt = n_lines - n50, per = (cnt + 31) / 32;
-        const int lo = n50 + lane * per, hi = min(lo + per, n_lines);
-        double tot = 1.0;
-        for (int n = lo; n < hi; ++n) tot *= sG[n];
-        double incl = tot;
-        for (int o = 1; o < 32; o <<= 1) {
-            double up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl *= up;
-        }
-        double carry = __shfl_up_sync(0xffffffffu, incl, 1);
-        const double seed = n50 > 0 ? sG[n50 - 1] : 0.0;              // flux_ratios[-1] of a zeroed array
-        double run = lane == 0 ? seed : seed * carry;
-        __syncwarp();
-        for (int n = lo; n < hi; ++n) { run *= sG[n]; sG[n] = run; }
-    }
-    if (do_bc && tid >= 32) {
-        const double tauBE = b_tau;
-        int nst = min(pl.bc_nstage, P);
+    // Balmer-continuum samples f0 for the staged pixels; loads batched four deep so one L2 round
+    // trip is exposed per batch instead of per pixel
+    if (do_bc) {
+        const int nst = min(pl.bc_nstage, P);
         const double inv_kT = 1.0 / kT;
-        for (int k = tid - 32; k < nst; k += kThreads - 32) sF0[k] = bc_f0<FULL>(pl, k, kT, inv_kT, tauBE);
+        for (int k0 = tid; k0 < nst; k0 += 4 * kThreads) {
+            double h[4], kk[4], t3[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = min(k0 + j * kThreads, nst - 1);
+                h[j] = pl.bc_hnu[k]; kk[j] = pl.bc_K[k]; t3[j] = pl.bc_t3[k];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = k0 + j * kThreads;
+                if (k < nst) sF0[k] = bc_f0<FULL>(h[j], kk[j], t3[j], kT, inv_kT, b_tau);
+            }
+        }
     }
     __syncthreads();
 
+    // (the ratio recursion flux_ratios[i] = flux_ratios[i-1] * exp(e_i / kT), BC:292-296, is telescoped:
+    //  r_n = r_50 * exp(sum_{m=51..n} e_m / kT); line_cum holds the partial sums, P3 applies r_50)
     // ---- P3: finish the line table; BC normaliser ---------------------------------------------
     if (do_bpc) {
+        const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
+        const double r50 = n50 > 0 ? sG[n50 - 1] : 0.0;               // flux_ratios[-1] of a zeroed array
         for (int n = tid; n < n_pad; n += kThreads) {
             int gq = n >> 2, r4 = n & 3;
             double wv = sW[n], rr = sG[n];
+            if (n >= n50) rr = r50 * rr;
             if (n < n_lines) {
                 sLine[gq * 12 + 4 + r4] = wv * wv;
                 sLine[gq * 12 + 8 + r4] = lorentz ? rr * wv : rr;
@@ -1524,6 +1520,14 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
             }
             if ((rc = upload(pl, d->balmer_line_center, pd.n_lines, &pd.line_c0))) return rc;
             if ((rc = upload(pl, d->balmer_line_exparg, pd.n_lines, &pd.line_e))) return rc;
+            {
+                std::vector<double> cum(pd.n_lines, 0.0);
+                long double acc = 0.0L;
+                for (int n = 0; n < pd.n_lines; ++n) {
+                    if (pd.line_min + n > 50) { acc += (long double)d->balmer_line_exparg[n]; cum[n] = (double)acc; }
+                }
+                if ((rc = upload(pl, cum.data(), pd.n_lines, &pd.line_cum))) return rc;
+            }
             memcpy(pd.sh_ne, d->sh95_ne, sizeof(pd.sh_ne));
             memcpy(pd.sh_T, d->sh95_T, sizeof(pd.sh_T));
             if (d->sh95_z)
