@@ -66,6 +66,7 @@ enum StatusBits : int {
 
 constexpr int kMaxClusters = 8;        // base clusters + nested supersets
 constexpr int kMom = 16;               // series terms kept (validated: <= 1e-15 at rho <= 0.1)
+constexpr int kMomPoly = 12;           // terms of the moment power series in z = S_ref / kT (|z| <= 0.2)
 struct ClusterDev {
     int g_lo, g_hi;                    // line groups (of 4) covered
     double cb0, R0;                    // centre and half-span at zero velocity offset
@@ -116,6 +117,11 @@ struct PlanDev {
     int series_on, n_clusters, n_super, g_direct_end;
     ClusterDev cl[kMaxClusters];          // [0,n_clusters) base, then n_super nested supersets, widest first
     const double* line_d[kMaxClusters];   // per cluster: scaled offsets (c_n - c_bar)/R of its lines
+    // n > 50 part of the cluster moments as a power series: sum_n c_n d_n^k exp(z u_n), u_n = S_n / S_ref,
+    // = sum_p z^p mom_G[cluster][k][p]; valid (<= 1e-17) while |S_ref| / (k_B Te_min) <= 0.2
+    const double* mom_G[kMaxClusters];
+    double mom_Sref;
+    int mom_poly;
     const double *bc_hnu, *bc_K, *bc_t3;
     const int4* bc_idx;                   // 4 source pixels of the log_conv stencil
     const double *bc_tb0, *bc_tb1, *bc_ta;
@@ -807,62 +813,62 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
 
     // (the ratio recursion flux_ratios[i] = flux_ratios[i-1] * exp(e_i / kT), BC:292-296, is telescoped:
     //  r_n = r_50 * exp(sum_{m=51..n} e_m / kT); line_cum holds the partial sums, P3 applies r_50)
-    // ---- P3: finish the line table; BC normaliser ---------------------------------------------
-    if (do_bpc) {
-        const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
-        const double r50 = n50 > 0 ? sG[n50 - 1] : 0.0;               // flux_ratios[-1] of a zeroed array
-        for (int n = tid; n < n_pad; n += kThreads) {
-            int gq = n >> 2, r4 = n & 3;
-            double wv = sW[n], rr = sG[n];
-            if (n >= n50) rr = r50 * rr;
-            if (n < n_lines) {
-                sLine[gq * 12 + 4 + r4] = wv * wv;
-                sLine[gq * 12 + 8 + r4] = lorentz ? rr * wv : rr;
-            } else {   // padding: contributes exactly 0
-                sLine[gq * 12 + 4 + r4] = 1.0;
-                sLine[gq * 12 + 8 + r4] = 0.0;
-            }
-        }
-    }
+    // ---- P3: finish the line table; BC and BpC normalisers; cluster moments -------------------------
+    const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
+    double bpc_scale = 0.0;
     if (do_bc && warp == 7 && lane == 0) {
-        double fnorm = bc_conv_at(pl, sF0, c.bc_istar);                  // BC:444
+        double fnorm = bc_conv_at(pl, sF0, bc_istar);                    // BC:444
         c.bc_scale = b_norm / fnorm;                                     // BC:446
         c.bc_finite = isfinite(c.bc_scale) ? 1 : 0;
     }
-    __syncthreads();
-
-    // ---- P4: BpC normaliser = the line sum at the edge pixel (BC:385), all threads ----------------
-    const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
-    double bpc_scale = 0.0;
     if (do_bpc) {
-        const double lam = pl.wl[bpc_istar];
+        const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
+        const double r50 = n50 > 0 ? sG[n50 - 1] : 0.0;               // flux_ratios[-1] of a zeroed array
+        // line table entries (w^2, a = ratio * w) and, on the way, the BpC normaliser = the line sum
+        // at the edge pixel (BC:385)
+        const double lam_e = pl.wl[bpc_istar];
         double s = 0.0;
-        for (int n = tid; n < n_lines; n += kThreads) {
-            int gq = n >> 2, r4 = n & 3;
-            double d = lam - sLine[gq * 12 + r4];
-            double w2 = sLine[gq * 12 + 4 + r4];
-            double a = sLine[gq * 12 + 8 + r4];
-            if (lorentz) s += a / (d * d + w2);
-            else s += a * exp_fast(-(d * d) / w2);
+        for (int n = tid; n < n_pad; n += kThreads) {
+            const int gq = n >> 2, r4 = n & 3;
+            const double wv = sW[n];
+            double rr = sG[n];
+            if (n >= n50) rr = r50 * rr;
+            double w2 = 1.0, a = 0.0;                                 // padding: contributes exactly 0
+            if (n < n_lines) {
+                w2 = wv * wv;
+                a = lorentz ? rr * wv : rr;
+                const double d = lam_e - sLine[gq * 12 + r4];
+                if (lorentz) s += a / (d * d + w2);
+                else s += a * exp_fast(-(d * d) / w2);
+            }
+            sLine[gq * 12 + 4 + r4] = w2;
+            sLine[gq * 12 + 8 + r4] = a;
         }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) c.red[warp] = s;
-        // cluster moments M_k = sum_n a_n d_n^k and per-walker cluster constants: one warp each
+        // cluster moments M_k = sum_n a_n d_n^k and per-walker cluster constants: one warp each.
+        // FULL with pl.mom_poly: the n > 50 lines, whose ratios are r_50 exp(S_n / kT), enter through
+        // the walker-independent power series in z = S_ref / kT (mom_G), so only the n <= 50 lines of
+        // the cluster are visited.
         const int n_cl = series_on && lorentz ? pl.n_clusters + pl.n_super : 0;
         if (warp < n_cl) {
             const ClusterDev& cd = pl.cl[warp];
             const double* dd = pl.line_d[warp];
+            const bool poly = FULL && pl.mom_poly;
+            const int n_end = poly ? min(cd.g_hi * 4, n50) : cd.g_hi * 4;
             double mk[kMom];
 #pragma unroll
             for (int k = 0; k < kMom; ++k) mk[k] = 0.0;
-            for (int n = cd.g_lo * 4 + lane; n < cd.g_hi * 4; n += 32) {
-                double pw = sLine[(n >> 2) * 12 + 8 + (n & 3)];      // a_n = r_n w_n
+            for (int n = cd.g_lo * 4 + lane; n < n_end; n += 32) {
+                double rr = sG[n];
+                if (n >= n50) rr = r50 * rr;
+                double pw = rr * sW[n];                               // a_n = r_n w_n (0 for padding)
                 const double dn = dd[n];
 #pragma unroll
                 for (int k = 0; k < kMom; ++k) { mk[k] += pw; pw *= dn; }
             }
             // lane sums of all 16 moments by a halving butterfly (16 shuffled doubles instead of 80;
-            // same xor tree 16, 8, 4, 2, 1 per moment): lane 2k ends up with moment k
+            // same xor tree 16, 8, 4, 2, 1 per moment): lanes 2k, 2k+1 end up with moment k
             static_assert(kMom == 16, "butterfly below is written for 16 moments");
 #pragma unroll
             for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
@@ -875,6 +881,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 }
             }
             mk[0] += __shfl_xor_sync(0xffffffffu, mk[0], 1);
+            if (poly) {
+                const double* G = pl.mom_G[warp] + (lane >> 1) * kMomPoly;
+                double g[kMomPoly];
+#pragma unroll
+                for (int q = 0; q < kMomPoly; ++q) g[q] = G[q];
+                const double z = pl.mom_Sref / kT;
+                double acc = g[kMomPoly - 1];
+#pragma unroll
+                for (int q = kMomPoly - 2; q >= 0; --q) acc = fma(acc, z, g[q]);
+                const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
+                mk[0] = fma(r50 * (width * (1.0 - shift)), acc, mk[0]);
+            }
             if (!(lane & 1)) c.cw[warp].mom[lane >> 1] = mk[0];
             if (lane == 0) {
                 const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
@@ -892,7 +910,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 cw.far_lam = cb + sqrt(fmax(cw.thr - cw.kcb2, 0.0)) * (1.0 + 1e-12);
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (do_bpc) {
         double tot = 0.0;
         for (int q = 0; q < kThreads / 32; ++q) tot += c.red[q];
         bpc_scale = b_norm / tot;                                        // BC:387
@@ -1527,6 +1547,39 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
                     if (pd.line_min + n > 50) { acc += (long double)d->balmer_line_exparg[n]; cum[n] = (double)acc; }
                 }
                 if ((rc = upload(pl, cum.data(), pd.n_lines, &pd.line_cum))) return rc;
+                // moment power series of the n > 50 lines (see PlanDev::mom_G)
+                pd.mom_poly = 0;
+                pd.mom_Sref = cum[pd.n_lines - 1];
+                const int n50 = std::min(std::max(51 - pd.line_min, 0), pd.n_lines);
+                int o_bal = -1;
+                for (int q = 0; q < pd.n_comp; ++q) if (pd.comp_kind[q] == SPAMM_COMP_BALMER) o_bal = pd.comp_off[q];
+                const double te_lo = (d->prior_lo && o_bal >= 0) ? d->prior_lo[o_bal + 1] : 0.0;
+                if (pd.series_on && n50 < pd.n_lines && pd.mom_Sref < 0.0 && te_lo > 0.0 &&
+                    std::fabs(pd.mom_Sref) / (d->kb_cgs * te_lo) <= 0.2) {
+                    const double* cc = d->balmer_line_center;
+                    for (int k = 0; k < pd.n_clusters + pd.n_super; ++k) {
+                        std::vector<long double> G((size_t)kMom * kMomPoly, 0.0L);
+                        const int lo = std::max(pd.cl[k].g_lo * 4, n50), hi = std::min(pd.cl[k].g_hi * 4, pd.n_lines);
+                        for (int n = lo; n < hi; ++n) {
+                            const long double dn = ((long double)cc[n] - (long double)pd.cl[k].cb0) / (long double)pd.cl[k].R0;
+                            const long double dn_dev = (long double)(double)dn;   // the device uses the rounded offset
+                            const long double un = (long double)cum[n] / (long double)pd.mom_Sref;
+                            long double dj = 1.0L;
+                            for (int j = 0; j < kMom; ++j) {
+                                long double up = 1.0L;                              // u^p / p!
+                                for (int q = 0; q < kMomPoly; ++q) {
+                                    G[(size_t)j * kMomPoly + q] += (long double)cc[n] * dj * up;
+                                    up *= un / (long double)(q + 1);
+                                }
+                                dj *= dn_dev;
+                            }
+                        }
+                        std::vector<double> Gd(G.size());
+                        for (size_t i = 0; i < G.size(); ++i) Gd[i] = (double)G[i];
+                        if ((rc = upload(pl, Gd.data(), Gd.size(), &pd.mom_G[k]))) return rc;
+                    }
+                    pd.mom_poly = 1;
+                }
             }
             memcpy(pd.sh_ne, d->sh95_ne, sizeof(pd.sh_ne));
             memcpy(pd.sh_T, d->sh95_T, sizeof(pd.sh_T));
