@@ -130,6 +130,7 @@ struct PlanDev {
     double bc_dlnew;
     double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
     int exp_safe;                         // the prior box bounds every exp() argument of the fused kernel
+    int nc_pair_ok;                       // P even and |slope| |ln(wl[i+1]/wl[i])| <= 0.016 inside the prior box
     int* status;
 };
 
@@ -432,7 +433,6 @@ struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     double kT, tauBE;
     int bc_istar, bpc_istar;
     int prior_ok;
-    int next_task;
     int bc_finite;       // bc_scale is finite: chunks without Balmer-continuum pixels may skip the 0 * scale
 };
 static_assert(sizeof(WalkerCtx) % 16 == 0, "line table must stay 16-byte aligned");
@@ -494,15 +494,21 @@ __device__ __forceinline__ void templ_sum_n(const TemplCoef* __restrict__ tc, in
 }
 
 // two families with compile-time counts (FULL model): all NA + NB row loads in one batch
-template <int NA, int NB>
+// (PAIR: the lane's two pixels are adjacent, one 16-byte load per row)
+template <int NA, int NB, bool PAIR>
 __device__ __forceinline__ void templ_sum_2(const TemplCoef* __restrict__ tc, int i0, double (&outa)[kPix],
                                             double (&outb)[kPix]) {
     double v[NA + NB][kPix];
 #pragma unroll
     for (int j = 0; j < NA + NB; ++j) {
         const double* f = tc[j].f + i0;
+        if (PAIR) {
+            const double2 t = *reinterpret_cast<const double2*>(f);
+            v[j][0] = t.x; v[j][kPix - 1] = t.y;
+        } else {
 #pragma unroll
-        for (int q = 0; q < kPix; ++q) v[j][q] = f[q * 32];
+            for (int q = 0; q < kPix; ++q) v[j][q] = f[q * 32];
+        }
     }
 #pragma unroll
     for (int q = 0; q < kPix; ++q) { outa[q] = 0.0; outb[q] = 0.0; }
@@ -628,7 +634,7 @@ constexpr int kChunk = 32 * kPix;      // pixels per warp task
 // FULL: compile-time view of the headline model (run_spamm's NC + Fe x3 + host x7 + BalmerCombined with
 // both parts on, Lorentzian lines, far-field series, bank rows): every component test, template count
 // and line-type branch below folds away, which roughly halves the non-FP64 instructions of a task.
-constexpr int kFullFe = 3, kFullHost = 7;
+constexpr int kFullFe = 3, kFullHost = 7, kFullClusters = 4, kFullSuper = 3;
 template <int MODE, bool CANON, bool SPLIT, bool FULL>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
@@ -654,7 +660,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const double* pw = params + (size_t)w * pl.D;
 
     // ---- P0: parameters + flat-box prior (Model.prior, Model.py:449-470) -----------------
-    if (tid == 0) { c.prior_ok = 1; c.next_task = 0; }
+    if (tid == 0) c.prior_ok = 1;
     __syncthreads();
     if (tid < pl.D) {
         double v = pw[tid];
@@ -690,6 +696,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const bool do_bpc = FULL ? true : have_balmer && pl.bpc_on;
     const bool lorentz = FULL ? true : pl.line_type == SPAMM_LINE_LORENTZIAN;
     const bool series_on = FULL ? true : pl.series_on != 0;
+    constexpr bool PAIR = FULL && kPix == 2;      // adjacent-pixel lanes with 16-byte loads
+    constexpr int QS = PAIR ? 1 : 32;             // pixel stride between a lane's pixels
+    const int n_base = FULL ? kFullClusters : pl.n_clusters, n_super = FULL ? kFullSuper : pl.n_super;
     const bool fe_rows_direct = FULL ? false : dr.fe_f != nullptr;
     const bool host_rows_direct = FULL ? false : dr.host_f != nullptr;
 
@@ -850,7 +859,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         // FULL with pl.mom_poly: the n > 50 lines, whose ratios are r_50 exp(S_n / kT), enter through
         // the walker-independent power series in z = S_ref / kT (mom_G), so only the n <= 50 lines of
         // the cluster are visited.
-        const int n_cl = series_on && lorentz ? pl.n_clusters + pl.n_super : 0;
+        const int n_cl = series_on && lorentz ? n_base + n_super : 0;
         if (warp < n_cl) {
             const ClusterDev& cd = pl.cl[warp];
             const double* dd = pl.line_d[warp];
@@ -921,29 +930,37 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const bool bc_finite = c.bc_finite != 0;
     double* fout = (MODE == 1) ? out + (size_t)wloc * P : nullptr;
 
-    // ---- main phase: each warp pulls 64-pixel tasks, reddest (line-heavy) chunks first ------------
+    // ---- main phase: 64-pixel warp tasks, reddest (line-heavy) chunks first -------------------------
     const int n_chunks = pl.n_chunks;
     const int n_groups = n_pad >> 2;
     const double2* sL2 = reinterpret_cast<const double2*>(sLine);
-    const uint32_t next_task_addr = (uint32_t)__cvta_generic_to_shared(&c.next_task);
-    for (;;) {
-        int t = 0;
-        if (lane == 0)      // plain atom.shared: the compiler's atomicAdd expands to a warp-aggregation sequence
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(next_task_addr) : "memory");
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (SPLIT) t = t * csize + crank;                     // tasks dealt round-robin over the cluster
-        if (t >= n_chunks) break;
+    // (static round-robin: a shared task counter costs a dozen instructions per task, and the cost of a
+    // task varies smoothly with its position, so every warp gets the same mix)
+    for (int t = SPLIT ? warp * csize + crank : warp; t < n_chunks; t += (kThreads / 32) * csize) {
         const int chunk = n_chunks - 1 - t;
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
-        const int i0 = chunk * kChunk + lane;
+        // PAIR (FULL kernel): lane l holds the adjacent pixels 2l, 2l+1 of the chunk, fetched with 16-byte
+        // loads; otherwise pixels l and l + 32
+        const int i0 = chunk * kChunk + (PAIR ? 2 * lane : lane);
         double m[kPix], post[kPix], acc[kPix];
         // every global load of the task is issued here, ahead of its first use, so one L2 round
         // trip is exposed per task instead of one per phase
         double lnhi[kPix], lnlo[kPix], lam[kPix], dat[kPix], ierr[kPix];
+        if (PAIR) {
+            const double2 a = *reinterpret_cast<const double2*>(pl.nc_lnx_hi + i0);
+            const double2 b = *reinterpret_cast<const double2*>(pl.nc_lnx_lo + i0);
+            const double2 l = *reinterpret_cast<const double2*>(pl.wl + i0);
+            const double2 d = *reinterpret_cast<const double2*>(pl.flux + i0);
+            const double2 e = *reinterpret_cast<const double2*>(pl.inv_err + i0);
+            lnhi[0] = a.x; lnhi[kPix - 1] = a.y; lnlo[0] = b.x; lnlo[kPix - 1] = b.y;
+            lam[0] = l.x; lam[kPix - 1] = l.y; dat[0] = d.x; dat[kPix - 1] = d.y;
+            ierr[0] = e.x; ierr[kPix - 1] = e.y;
+        }
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
             acc[q] = 0.0;
             post[q] = 0.0;
+            if (PAIR) continue;
             lnhi[q] = has_nc ? pl.nc_lnx_hi[i0 + 32 * q] : 0.0;
             lnlo[q] = has_nc ? pl.nc_lnx_lo[i0 + 32 * q] : 0.0;
             lam[q] = pl.wl[i0 + 32 * q];
@@ -953,20 +970,35 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         {
             double fe_v[kPix], host_v[kPix], nc_v[kPix];
             if (FULL) {
-                templ_sum_2<kFullFe, kFullHost>(c.tc, i0, fe_v, host_v);
+                templ_sum_2<kFullFe, kFullHost, PAIR>(c.tc, i0, fe_v, host_v);
             } else {
                 if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
                 if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
             }
+            if (PAIR) {
+                // second pixel of the pair from the first: x1^-s = x0^-s exp(z), z = -s (ln x1 - ln x0);
+                // |z| <= 0.016 (PlanDev::nc_pair_ok), degree-6 Taylor: <= 4e-17
+                nc_v[0] = nc_flux<true>(pl, c, i0, lnhi[0], lnlo[0], false);
+                const double ms = -c.nc_slope1;
+                const double z = fma(ms, lnlo[kPix - 1] - lnlo[0], ms * (lnhi[kPix - 1] - lnhi[0]));
+                double pz = fma(z, 1.0 / 720.0, 1.0 / 120.0);
+                pz = fma(pz, z, 1.0 / 24.0);
+                pz = fma(pz, z, 1.0 / 6.0);
+                pz = fma(pz, z, 0.5);
+                pz = fma(pz, z, 1.0);
+                pz = fma(pz, z, 1.0);
+                nc_v[kPix - 1] = nc_v[0] * pz;
+            } else {
 #pragma unroll
-            for (int q = 0; q < kPix; ++q)
-                nc_v[q] = has_nc ? nc_flux<FULL>(pl, c, i0 + 32 * q, lnhi[q], lnlo[q], nc_broken) : 0.0;
+                for (int q = 0; q < kPix; ++q)
+                    nc_v[q] = has_nc ? nc_flux<FULL>(pl, c, i0 + QS * q, lnhi[q], lnlo[q], nc_broken) : 0.0;
+            }
             if (CANON) {
                 // model_spectrum.flux starts at zero and adds NC, Fe, host in turn (Model.py:350-380)
 #pragma unroll
                 for (int q = 0; q < kPix; ++q) {
                     double v = 0.0;
-                    if (has_nc) v = v + nc_v[q];
+                    if (has_nc) v = FULL ? nc_v[q] : v + nc_v[q];      // (0.0 + x == x up to the sign of zero)
                     if (n_fe) v = v + fe_v[q];
                     if (n_host) v = v + host_v[q];
                     m[q] = v;
@@ -1006,14 +1038,15 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                     // pixel of the task absorbs all its lines
                     // (lane 0 holds the task's first pixel, the nearest one when the task is redward of c_bar)
                     const double lam_first = __shfl_sync(0xffffffffu, lam[0], 0);
-                    for (int sidx = 0; sidx < pl.n_super; ++sidx) {
-                        if (lam_first >= c.cw[pl.n_clusters + sidx].far_lam) { sup = pl.n_clusters + sidx; break; }
+#pragma unroll
+                    for (int sidx = kFullSuper - 1; sidx >= 0; --sidx) {     // widest far superset wins
+                        if (sidx < n_super && lam_first >= c.cw[n_base + sidx].far_lam) sup = n_base + sidx;
                     }
                     if (sup >= 0) {
                         const double u = lam_first - c.cw[sup].cb;
                         sup_cmin = fma(u, u, c.cw[sup].kcb2);
                     }
-                    nseg = sup >= 0 ? 2 : 1 + pl.n_clusters;
+                    nseg = sup >= 0 ? 2 : 1 + n_base;
                 }
 #pragma unroll 1
                 for (int sg = 0; sg < nseg; ++sg) {
@@ -1051,7 +1084,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         double chi = 0.0;
 #pragma unroll
         for (int q = 0; q < kPix; ++q) {
-            const int i = i0 + 32 * q;
+            const int i = i0 + QS * q;
             double v = m[q];
             if (have_balmer) {
                 double bc = 0.0, bpc = 0.0;
@@ -1082,7 +1115,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double s = 0.0;
             for (int k = lane; k < n_chunks; k += 32) {
                 if (SPLIT) {
-                    // chunk k was task t = n_chunks-1-k, handled by cluster rank t % csize
+                    // chunk k was task t = n_chunks-1-k, handled by cluster rank t % csize (see the task loop)
                     const double* peer = cooperative_groups::this_cluster().map_shared_rank(
                         sChi, (unsigned)((n_chunks - 1 - k) % csize));
                     s += peer[k];
@@ -1659,6 +1692,7 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     // drop the range checks.  NC: |slope| max|ln(wl/wl0)|; BC: h nu / (k Te) at the bluest pixel and
     // Te_min; tau_BE (wl/edge)^3 over the staged pixels.
     pd.exp_safe = 0;
+    pd.nc_pair_ok = 0;
     if (d->prior_lo && d->prior_hi && seen[SPAMM_COMP_NUCLEAR] && seen[SPAMM_COMP_BALMER] && !d->nc_broken_pl &&
         pd.bc_on) {
         int o_nc = -1, o_bal = -1;
@@ -1676,6 +1710,9 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         const bool ok = smax * lmax < 690.0 && te_lo > 0.0 && hnu0 / (d->kb_cgs * te_lo) < 690.0 &&
                         taumax * t3max < 690.0;
         pd.exp_safe = ok ? 1 : 0;    // NaN bounds compare false
+        double dmax = 0.0;
+        for (int i = 0; i + 1 < P; ++i) dmax = std::max(dmax, std::fabs(std::log(d->wl[i + 1] / d->wl[i])));
+        pd.nc_pair_ok = (P % 2 == 0 && smax * dmax <= 0.016) ? 1 : 0;
     }
 
     // shared memory of the fused kernel
@@ -1818,7 +1855,8 @@ static bool full_model(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, co
     return pd.comp_kind[0] == SPAMM_COMP_NUCLEAR && pd.comp_kind[1] == SPAMM_COMP_FE &&
            pd.comp_kind[2] == SPAMM_COMP_HOST && pd.comp_kind[3] == SPAMM_COMP_BALMER && !pd.nc_broken &&
            pd.fe.n_templ == kFullFe && pd.host.n_templ == kFullHost && pd.bc_on && pd.bpc_on &&
-           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on && pd.exp_safe && pd.lo != nullptr;
+           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on && pd.exp_safe && pd.lo != nullptr &&
+           pd.n_clusters == kFullClusters && pd.n_super == kFullSuper && pd.nc_pair_ok;
 }
 
 template <int MODE>
