@@ -367,19 +367,22 @@ def run_ours(args):
         wl = np.asarray(model.data_spectrum.spectral_axis)
         flops = algorithmic_flops(wl, FE_RANGES)
         achieved = flops * (n_local * args.steps / (total_ms * 1e-3)) / 1e12    # this GPU's share
-        traffic = None
+        traffic, pipe_busy = None, None
         tpath = os.path.join(ROOT, "profiles", "k_walkers_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic, pipe_busy = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_busy_default")
         roofline = {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
                     "frac": achieved / float(peak.value) if peak.value else None, "traffic": traffic,
                     "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); "
                                    "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
-                    "algorithmic_flops_per_eval": flops, "kernel": "k_walkers<0>",
+                    "algorithmic_flops_per_eval": flops,
+                    "kernel": "k_walkers<0, true, false, true> (headline-model instantiation)",
                     "note": "achieved = SURVEY 8(d) algorithmic flops x evals/s; the default kernel sums "
-                            "distant Balmer-line clusters by a far-field series and executes ~6x fewer "
+                            "distant Balmer-line clusters by a far-field series and executes ~8x fewer "
                             "flops than that count, so frac can exceed 1; exact_line_sum below is the "
-                            "kernel that executes them all"}
+                            "kernel that executes them all",
+                    "fp64_pipe_busy_ncu": pipe_busy}
         # HBM view, for completeness: 168 algorithmic bytes per evaluation (params in, ln-prob out)
         hbm_peak = None
         mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
