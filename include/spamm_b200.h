@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SPAMM_ABI_VERSION 1
+#define SPAMM_ABI_VERSION 2
 #define SPAMM_MAX_COMPONENTS 8
 #define SPAMM_MAX_TEMPLATES 16
 #define SPAMM_SH95_NE 7
@@ -42,7 +42,8 @@ enum SpammComponentKind {
     SPAMM_COMP_NUCLEAR = 0,  /* NuclearContinuumComponent */
     SPAMM_COMP_FE = 1,       /* FeComponent               */
     SPAMM_COMP_HOST = 2,     /* HostGalaxyComponent       */
-    SPAMM_COMP_BALMER = 3    /* BalmerCombined            */
+    SPAMM_COMP_BALMER = 3,   /* BalmerCombined            */
+    SPAMM_COMP_EXTINCTION = 4 /* Extinction (spamm/components/ReddeningLaw.py:126-216); must be last */
 };
 
 enum SpammLineType { SPAMM_LINE_LORENTZIAN = 0, SPAMM_LINE_GAUSSIAN = 1 };
@@ -118,6 +119,12 @@ typedef struct SpammPlanDesc {
     double c_kms, c_cgs, c_aa, h_cgs, kb_cgs, balmer_edge;
 
     int32_t max_walkers;                       /* workspace is sized for this many walkers per call */
+
+    /* Extinction (ReddeningLaw.py): k(lambda) [P] of the selected law as the host evaluated it
+     * (Calzetti_ext :7-20, LMC :22-46, MW :48-72, SMC :74-98, AGN :100-123; zeros = no law);
+     * the kernel multiplies the flux summed so far by pow(10, -0.4 * E(B-V) * k), Model.py:384-395.
+     * One parameter, E(B-V).  NULL unless a SPAMM_COMP_EXTINCTION is present. */
+    const double* ext_k;
 } SpammPlanDesc;
 
 typedef struct SpammPlan SpammPlan;

@@ -118,16 +118,52 @@ class Templates(object):
 # ----------------------------------------------------------------------------
 # the model
 # ----------------------------------------------------------------------------
-class OracleModel(object):
-    """Restates Model + the four components for one data spectrum.
+def extinction_k(wl, law):
+    """k(lambda) of the five curves of spamm/components/ReddeningLaw.py, so that the extinction is
+    pow(10, -0.4 * E(B-V) * k): Calzetti_ext :7-20 (k = 0, i.e. ext = 1, outside 0.12-2.2 um),
+    LMC_Fitzpatrick_ext :22-46, MW_Seaton_ext :48-72, SMC_Gordon_ext :74-98 (its far-UV C4 is
+    0.26, not the 0.46 declared above the loop), AGN_Gaskell_ext :100-123 (all wavelengths: the
+    range test is commented out).  Scalar arithmetic in the reference's operation order."""
+    wl = np.asarray(wl, dtype=np.float64)
+    if law == "AGN":                       # the one curve the reference evaluates on whole arrays (:118-122)
+        A, B, C, D, E, F, Rv = 0.000843, -0.02496, 0.2919, -1.815, 6.83, -7.92, 5.0
+        x = pow(np.array(wl / 10000.), -1)
+        return A * x ** 5 + B * x ** 4 + C * x ** 3 + D * x ** 2 + E * x + F + Rv
+    k = np.zeros(len(wl))
+    for j in range(len(wl)):
+        um = wl[j] / 10000.
+        if law == "Calzetti":
+            if (um >= 0.12) & (um < 0.63):
+                k[j] = 2.659 * (-1.857 + 1.040 / um) + 4.05
+            if (um >= 0.63) & (um <= 2.2):
+                k[j] = 2.659 * (-2.156 + 1.509 / um - 0.198 / pow(um, 2) + 0.11 / pow(um, 3)) + 4.05
+        elif law in ("LMC", "MW", "SMC"):
+            C1, C2, C3, C4uv, x_0, gamma, Rv = {
+                "LMC": (-0.69, 0.89, 2.55, 0.50, 4.608, 0.994, 3.1),
+                "MW": (-0.38, 0.74, 3.96, 0.26, 4.595, 1.051, 3.1),
+                "SMC": (-4.96, 2.26, 0.39, 0.26, 4.6, 1.0, 2.74)}[law]
+            x = pow(um, -1)
+            x2 = pow(x, 2)
+            D = x2 / (pow(x2 - pow(x_0, 2), 2) + x2 * pow(gamma, 2))
+            F = 0.5392 * pow((x - 5.9), 2) + 0.05644 * pow((x - 5.9), 3)
+            C4 = C4uv if x >= 5.9 else 0.0
+            k[j] = C1 + Rv + C2 * x + C3 * x * D + C4 * F
+        else:
+            raise KeyError(law)
+    return k
 
-    comps: ordered list drawn from "PL", "FE", "HOST", "BC" (the order fixes the
+
+class OracleModel(object):
+    """Restates Model + the components for one data spectrum.
+
+    comps: ordered list drawn from "PL", "FE", "HOST", "BC", "EXT" (the order fixes the
     parameter layout exactly like Model.components, spamm/Model.py:353-364;
-    run_spamm.py:100-122 appends PL, FE, HOST, BC).
+    run_spamm.py:100-125 appends PL, FE, HOST, BC, Extinction).  "EXT" multiplies the flux
+    accumulated so far by the `ext_law` curve (Model.py:358-361, 384-395).
     """
 
     def __init__(self, wl, flux, err, comps=("PL", "FE", "HOST", "BC"), bc=True, bpc=True,
-                 broken_pl=False, line_type=None, templates=None, pars=None):
+                 broken_pl=False, line_type=None, templates=None, pars=None, ext_law=None):
         self.wl = np.asarray(wl, dtype=np.float64)
         self.flux = np.asarray(flux, dtype=np.float64)
         self.err = np.asarray(err, dtype=np.float64)
@@ -138,6 +174,9 @@ class OracleModel(object):
         self.line_type = line_type or self.pars["balmer_continuum"]["bc_line_type"]
         self.tpl = templates if templates is not None else Templates()
         self.norm_wl = np.median(self.wl)                     # Spectrum.py:84-87
+        self.ext_law = ext_law
+        # Extinction.extinction :188-205: no law selected => [1.] * P
+        self.ext_k = extinction_k(self.wl, ext_law) if ext_law else np.zeros(len(self.wl))
         self._bounds = None
         self._init_templates()
 
@@ -173,11 +212,13 @@ class OracleModel(object):
                     + ["hg_stellar_disp"]
             elif c == "BC":
                 out += ["bc_norm", "bc_Te", "bc_tauBE", "bc_loffset", "bc_lwidth", "bc_logNe"]
+            elif c == "EXT":
+                out += ["E(B-V)"]                                  # ReddeningLaw.py:133
         return out
 
     def count(self, c):
         return {"PL": 4 if self.broken_pl else 2, "FE": len(self.log_fe) + 1,
-                "HOST": len(self.log_host) + 1, "BC": 6}[c]
+                "HOST": len(self.log_host) + 1, "BC": 6, "EXT": 1}[c]
 
     @property
     def ndim(self):
@@ -243,6 +284,9 @@ class OracleModel(object):
                        p["bc_lwidth_min"], p["bc_logNe_min"]]
                 hi += [nmax, p["bc_Te_max"], p["bc_tauBE_max"], p["bc_loffset_max"],
                        p["bc_lwidth_max"], p["bc_logNe_max"]]
+            elif c == "EXT":
+                lo += [0]                                            # ReddeningLaw.py:160-162
+                hi += [2.]
         self._bounds = (np.array(lo, dtype=np.float64), np.array(hi, dtype=np.float64))
         return self._bounds
 
@@ -268,6 +312,8 @@ class OracleModel(object):
             elif c in ("FE", "HOST"):
                 out += rng.uniform(low=l[0], high=h[0], size=n - 1).tolist()
                 out.append(rng.uniform(low=l[-1], high=h[-1]))
+            elif c == "EXT":
+                out.append(rng.uniform(low=l[0], high=h[0]))          # ReddeningLaw.py:163-165
             else:
                 for i in range(6):
                     out.append(rng.uniform(low=l[i], high=h[i]))
@@ -416,7 +462,15 @@ class OracleModel(object):
             return self.bpc_flux(p)
         raise ValueError("BalmerCombined needs BC and/or BpC")   # reference: UnboundLocalError
 
+    def extinction(self, p):
+        """Extinction.extinction :188-205: pow(10, -0.4 * E(B-V) * k) per pixel (AGN: on the array)."""
+        if self.ext_law == "AGN":
+            return pow(10, -0.4 * p[0] * self.ext_k)
+        return np.array([pow(10, -0.4 * p[0] * kj) for kj in self.ext_k])
+
     def component_flux(self, c, p):
+        if c == "EXT":
+            return np.zeros(len(self.wl))                          # Extinction.flux :180-185
         return {"PL": self.nc_flux, "FE": self.fe_flux, "HOST": self.host_flux,
                 "BC": self.balmer_flux}[c](np.asarray(p, dtype=np.float64))
 
@@ -428,7 +482,10 @@ class OracleModel(object):
         k = 0
         for c in self.comps:
             n = self.count(c)
-            f += self.component_flux(c, params[k:k + n])
+            if c == "EXT":
+                f = np.array(f) * self.extinction(params[k:k + n])   # Model.reddening :384-395
+            else:
+                f += self.component_flux(c, params[k:k + n])
             k += n
         return f
 

@@ -9,12 +9,12 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPAMM_B200_LIB", os.path.join(PKG, "libspamm_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_COMPONENTS = 8
 MAX_TEMPLATES = 16
 SH95_NE, SH95_T, SH95_LINES = 7, 10, 48
 
-COMP_NUCLEAR, COMP_FE, COMP_HOST, COMP_BALMER = 0, 1, 2, 3
+COMP_NUCLEAR, COMP_FE, COMP_HOST, COMP_BALMER, COMP_EXTINCTION = 0, 1, 2, 3, 4
 LINE_LORENTZIAN, LINE_GAUSSIAN = 0, 1
 TEMPLATES_AUTO, TEMPLATES_BANK, TEMPLATES_DIRECT = 0, 1, 2
 
@@ -75,6 +75,7 @@ class SpammPlanDesc(ctypes.Structure):
         ("kb_cgs", ctypes.c_double),
         ("balmer_edge", ctypes.c_double),
         ("max_walkers", ctypes.c_int32),
+        ("ext_k", c_double_p),
     ]
 
 

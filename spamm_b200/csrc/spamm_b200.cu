@@ -129,6 +129,9 @@ struct PlanDev {
     int bc_nstage;
     double bc_dlnew;
     double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
+    // Extinction (ReddeningLaw.py): k(lambda) of the selected curve, E(B-V) parameter offset; null = absent
+    const double* ext_k;
+    int ext_off, ext_q;
     int exp_safe;                         // the prior box bounds every exp() argument of the fused kernel
     int nc_pair_ok;                       // P even and |slope| |ln(wl[i+1]/wl[i])| <= 0.016 inside the prior box
     int* status;
@@ -686,6 +689,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         else if (kind == SPAMM_COMP_HOST) has_host = true;
         else if (kind == SPAMM_COMP_BALMER) { off_bal = pl.comp_off[q]; q_bal = q; }
     }
+    // Extinction is the last component (run_spamm.py:123-125) and multiplies the flux summed so far
+    // (Model.py:358-361, 384-395); selected alone (component flux API) it returns the curve itself
+    const bool has_ext = !FULL && pl.ext_k != nullptr && ((mask >> pl.ext_q) & 1u);
+    const bool ext_alone = has_ext && (mask & ~(1u << pl.ext_q)) == 0u;
     if (FULL) { has_fe = true; has_host = true; }
     const bool has_nc = FULL ? true : off_nc >= 0;
     const bool nc_broken = FULL ? false : pl.nc_broken != 0;
@@ -1011,6 +1018,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 for (int k = 0; k < pl.n_comp; ++k) {
                     if (!((mask >> k) & 1u) || k == q_bal) continue;
                     const int kind = pl.comp_kind[k];
+                    if (kind == SPAMM_COMP_EXTINCTION) continue;
 #pragma unroll
                     for (int q = 0; q < kPix; ++q) {
                         const double v = kind == SPAMM_COMP_NUCLEAR ? nc_v[q]
@@ -1093,6 +1101,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
             if (!CANON && q_bal + 1 < pl.n_comp) v = v + post[q];
+            if (has_ext) {
+                const double e = pow(10.0, (-0.4 * c.p[pl.ext_off]) * pl.ext_k[i]);   // ReddeningLaw.py:19,45,71,97,122
+                v = (ext_alone ? 1.0 : v) * e;
+            }
             const bool live = i < P;
             if (MODE == 0) {
                 double r = (dat[q] - v) * ierr[q];                                              // Model.py:440
@@ -1461,19 +1473,28 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
 
     // component layout
     pd.n_comp = d->n_components;
-    int off = 0, seen[4] = {0, 0, 0, 0};
+    int off = 0, seen[5] = {0, 0, 0, 0, 0};
+    pd.ext_k = nullptr; pd.ext_off = 0; pd.ext_q = 0;
     int off_fe = -1, off_host = -1;
     for (int q = 0; q < d->n_components; ++q) {
         int kind = d->component_kind[q];
-        if (kind < 0 || kind > 3) return set_error(SPAMM_EINVAL, "unknown component kind");
+        if (kind < 0 || kind > 4) return set_error(SPAMM_EINVAL, "unknown component kind");
         if (seen[kind]++) return set_error(SPAMM_EINVAL, "each component kind may appear once");
         pd.comp_kind[q] = kind;
         pd.comp_off[q] = off;
         if (kind == SPAMM_COMP_NUCLEAR) off += d->nc_broken_pl ? 4 : 2;
         else if (kind == SPAMM_COMP_FE) { off_fe = off; off += d->fe.n_templates + 1; }
         else if (kind == SPAMM_COMP_HOST) { off_host = off; off += d->host.n_templates + 1; }
-        else off += 6;
+        else if (kind == SPAMM_COMP_EXTINCTION) {
+            if (q != d->n_components - 1)
+                return set_error(SPAMM_EINVAL, "Extinction must be the last component (run_spamm.py:123-125)");
+            if (!d->ext_k) return set_error(SPAMM_EINVAL, "missing extinction curve");
+            pd.ext_off = off; pd.ext_q = q;
+            off += 1;
+        } else off += 6;
     }
+    if (seen[SPAMM_COMP_EXTINCTION])
+        if ((rc = upload(pl, d->ext_k, P, &pd.ext_k))) return rc;
     if (off != d->n_dim) return set_error(SPAMM_EINVAL, "n_dim does not match the component list");
 
     // NC: ln(wl / norm_wl) in double-double (PowerLaw1D evaluates (x / x_0) ** (-alpha))

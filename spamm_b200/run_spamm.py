@@ -15,17 +15,19 @@ from .components.NuclearContinuumComponent import NuclearContinuumComponent
 from .components.HostGalaxyComponent import HostGalaxyComponent
 from .components.FeComponent import FeComponent
 from .components.BalmerContinuumCombined import BalmerCombined
+from .components.ReddeningLaw import Extinction
 
-# the reference also lists five *_EXT reddening laws, which it cannot run (NameError at
-# run_spamm.py:124); they are rejected here with a clear message instead
-ACCEPTED_COMPS = ["PL", "FE", "HOST", "BC", "BPC"]
+# (the reference lists the five *_EXT reddening laws too but cannot run them: NameError at
+# run_spamm.py:124; here they append an Extinction component as that line intends)
+ACCEPTED_COMPS = ["PL", "FE", "HOST", "BC", "BPC", "CALZETTI_EXT", "SMC_EXT", "MW_EXT", "AGN_EXT", "LMC_EXT"]
 
 
 def spamm(complist, inspectrum, par_file=None, n_walkers=30, n_iterations=500, outdir=None,
           picklefile=None, comp_params=None, seed=None, save=True):
     """
     Args:
-        complist (list): component names, case insensitive: PL, FE, HOST, BC, BPC.
+        complist (list): component names, case insensitive: PL, FE, HOST, BC, BPC and at most one
+            reddening law of CALZETTI_EXT, SMC_EXT, MW_EXT, AGN_EXT, LMC_EXT.
         inspectrum (Spectrum or tuple): a Spectrum, or (wavelength, flux[, flux_error]).
         par_file (str): parameter file in the reference's yaml schema.
         n_walkers, n_iterations (int): ensemble size and chain length.
@@ -73,6 +75,10 @@ def spamm(complist, inspectrum, par_file=None, n_walkers=30, n_iterations=500, o
         model.components.append(BalmerCombined(pars=pars["balmer_continuum"],
                                                BalmerContinuum=components["BC"],
                                                BalmerPseudocContinuum=components["BPC"]))
+    if any(components[k] for k in ACCEPTED_COMPS[5:]):
+        model.components.append(Extinction(MW=components["MW_EXT"], AGN=components["AGN_EXT"],
+                                           LMC=components["LMC_EXT"], SMC=components["SMC_EXT"],
+                                           Calzetti=components["CALZETTI_EXT"]))
     model.data_spectrum = spectrum
 
     model.run_mcmc(n_walkers=n_walkers, n_iterations=n_iterations, seed=seed)

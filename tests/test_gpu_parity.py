@@ -463,3 +463,42 @@ def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
     for split in (2, 8):
         m_full.plan.set_walker_split(split)
         assert np.array_equal(m_full.lnposterior_batch(c.params), got)
+
+
+def test_extinction_component_vs_reference_golden():
+    """Extinction (ReddeningLaw.py): curves of the five laws from the device, and ln-posterior /
+    model flux of models ending with an Extinction, against the reference-made fixtures."""
+    from spamm_b200.Model import Model
+    from spamm_b200.Spectrum import Spectrum
+    from spamm_b200.components.ReddeningLaw import Extinction
+    z = np.load(os.path.join(GOLDEN, "extinction.npz"))
+    for g in ("g4096", "wide", "test7"):
+        wl = z["curve/%s/wl" % g]
+        sp = Spectrum(wl, wl, wl)
+        for law in ("MW", "AGN", "LMC", "SMC", "Calzetti"):
+            ext = Extinction(**{law: True})
+            for ebv in ("0.1", "0.7", "1.9"):
+                got = ext.extinction(spectrum=sp, params=[float(ebv)])
+                assert rel_err(got, z["curve/%s/%s/%s" % (g, law, ebv)]).max() < 1e-13, (g, law, ebv)
+    assert np.all(Extinction().extinction(spectrum=sp, params=[0.5]) == 1.0)
+    names = sorted({k.split("/")[1] for k in z.files if k.startswith("model/")})
+    for n in names:
+        g = lambda k: z["model/%s/%s" % (n, k)]  # noqa: E731
+        m = Model()
+        m.components += _components([str(c) for c in g("comps")])
+        m.components.append(Extinction(**{str(g("law")): True}))
+        m.data_spectrum = Spectrum(g("wl"), g("flux"), g("err"))
+        assert m.total_parameter_count == g("params").shape[1]
+        got = m.lnposterior_batch(g("params"))
+        assert rel_err(got, g("lnpost")).max() < LNPOST_RTOL, (n, got, g("lnpost"))
+        f = m.model_flux_batch(g("params")[:4])
+        assert np.max(np.abs(f - g("model_flux"))) <= FLUX_RTOL * np.max(np.abs(g("model_flux")))
+        # the prior, component by component, through the reference-shaped host API
+        p = g("params")[0]
+        assert np.isfinite(m.prior(p)) == np.isfinite(g("lnpost")[0])
+    # Extinction anywhere but last is rejected
+    bad = Model()
+    bad.components += [Extinction(MW=True)] + _components(["PL"])
+    bad.data_spectrum = Spectrum(g("wl"), g("flux"), g("err"))
+    with pytest.raises(Exception):
+        bad.lnposterior_batch(g("params")[:1, ::-1].copy())

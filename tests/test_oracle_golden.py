@@ -117,3 +117,33 @@ def test_stretch_move_recovers_gaussian():
     assert np.all(np.abs(s.mean(0) - mu) < 0.1 * sig)
     assert np.all(np.abs(s.std(0) / sig - 1) < 0.1)
     assert 0.5 < acc.mean() < 0.9
+
+
+def test_extinction_oracle_vs_reference_fixtures():
+    """Extinction component (ReddeningLaw.py): the five curves and models that end with an Extinction
+    against fixtures made by the unmodified reference (tests/golden/make_golden_ext.py)."""
+    from oracle.spamm_numpy import OracleModel, extinction_k
+    z = np.load(os.path.join(GOLDEN, "extinction.npz"))
+    n_curves = 0
+    for key in z.files:
+        if key.startswith("curve/") and key.count("/") == 3:
+            _, g, law, ebv = key.split("/")
+            o = OracleModel(z["curve/%s/wl" % g], z["curve/%s/wl" % g], z["curve/%s/wl" % g],
+                            comps=["EXT"], ext_law=law)
+            assert np.array_equal(o.ext_k, extinction_k(z["curve/%s/wl" % g], law))
+            got = o.extinction([float(ebv)])
+            assert rel_err(got, z[key]).max() < 1e-14, key
+            n_curves += 1
+    assert n_curves == 45
+    names = sorted({k.split("/")[1] for k in z.files if k.startswith("model/")})
+    assert len(names) == 5
+    for n in names:
+        g = lambda k: z["model/%s/%s" % (n, k)]  # noqa: E731
+        o = OracleModel(g("wl"), g("flux"), g("err"), comps=[str(c) for c in g("comps")] + ["EXT"],
+                        ext_law=str(g("law")))
+        lo, hi = o.bounds()
+        assert np.allclose(lo, g("lo"), rtol=1e-15, atol=0) and np.allclose(hi, g("hi"), rtol=1e-15, atol=0)
+        got = o.ln_posterior_batch(g("params"))
+        assert rel_err(got, g("lnpost")).max() < 1e-12, n
+        mf = np.array([o.model_flux(p) for p in g("params")[:4]])
+        assert np.max(np.abs(mf - g("model_flux"))) <= 2e-14 * np.max(np.abs(g("model_flux")))
