@@ -176,6 +176,10 @@ int spamm_plan_n_dim(const SpammPlan* plan);
 int spamm_plan_n_pix(const SpammPlan* plan);
 int spamm_plan_template_mode(const SpammPlan* plan);          /* resolved SpammTemplateMode */
 int spamm_plan_bank_rows(const SpammPlan* plan);              /* rows in the sigma bank */
+/* 1 if ln-posterior calls on this plan run the compile-time specialised instantiation of the fused
+ * kernel (the headline model: NC + Fe x3 + host x7 + BalmerCombined, Lorentzian lines, bank rows, a
+ * prior box bounding every exp argument, even P), 0 if the generic one. */
+int spamm_plan_specialised(const SpammPlan* plan);
 /* Device status word (0 = ok); synchronises `stream`.  Non-zero means some walker
  * needed a table entry outside the plan (SPAMM_ERANGE conditions). */
 int spamm_plan_status(SpammPlan* plan, void* stream);

@@ -83,7 +83,7 @@ class SpammPlanDesc(ctypes.Structure):
 EXPORTS = [
     "spamm_plan_create", "spamm_plan_destroy", "spamm_lnpost_batch", "spamm_lnpost_batch_host", "spamm_lnpost_batch_p2p",
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
-    "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split",
+    "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split", "spamm_plan_specialised",
     "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record",
     "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version",
 ]
@@ -123,7 +123,7 @@ def load():
     lib.spamm_likelihood_batch.argtypes = [vp, vp, i32, vp, vp]
     lib.spamm_likelihood_batch.restype = ctypes.c_int
     for name in ("spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
-                 "spamm_plan_bank_rows"):
+                 "spamm_plan_bank_rows", "spamm_plan_specialised"):
         getattr(lib, name).argtypes = [vp]
         getattr(lib, name).restype = ctypes.c_int
     lib.spamm_plan_status.argtypes = [vp, vp]

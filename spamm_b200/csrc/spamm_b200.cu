@@ -1880,6 +1880,13 @@ static bool full_model(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, co
            pd.n_clusters == kFullClusters && pd.n_super == kFullSuper && pd.nc_pair_ok;
 }
 
+extern "C" int spamm_plan_specialised(const SpammPlan* pl) {
+    if (!pl) return SPAMM_EINVAL;
+    DirectRows none{nullptr, nullptr, nullptr, nullptr};
+    const bool bank = pl->template_mode != SPAMM_TEMPLATES_DIRECT;
+    return bank && full_model(pl, pl->dev, (1u << pl->dev.n_comp) - 1u, none) ? 1 : 0;
+}
+
 template <int MODE>
 static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, const PlanDev& pd,
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,

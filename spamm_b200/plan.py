@@ -104,6 +104,11 @@ class ModelPlan(object):
     def launch_count(self):
         return int(self.lib.spamm_plan_launch_count(self._h))
 
+    @property
+    def specialised(self):
+        """True if ln-posterior calls run the specialised (FULL) instantiation of the fused kernel."""
+        return bool(self.lib.spamm_plan_specialised(self._h))
+
     def set_walker_split(self, mode):
         """0: one CTA per walker always; 1: automatic cluster split for small ensembles; 2/4/8: forced."""
         _lib.check(self.lib.spamm_plan_set_walker_split(self._h, int(mode)))

@@ -453,9 +453,11 @@ def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
     c = Case(z, "cfg5_full")
     m_full = _model(c)
     got = m_full.lnposterior_batch(c.params)
+    assert m_full.plan.specialised
     monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
     m_gen = _model(c)
     ref = m_gen.lnposterior_batch(c.params)
+    assert not m_gen.plan.specialised
     monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
     assert rel_err(got, ref).max() < 1e-13
     assert np.array_equal(np.isneginf(got), np.isneginf(ref))
@@ -502,3 +504,55 @@ def test_extinction_component_vs_reference_golden():
     bad.data_spectrum = Spectrum(g("wl"), g("flux"), g("err"))
     with pytest.raises(Exception):
         bad.lnposterior_batch(g("params")[:1, ::-1].copy())
+
+
+def test_specialised_kernel_on_awkward_grids(monkeypatch):
+    """Even-sized grids that the specialised (FULL) instantiation accepts but that stress its edges:
+    entirely blueward / redward of the Balmer edge, a single task, a ragged last task, the edge inside
+    the first and the last task; each against the oracle, the generic instantiation and every walker
+    split."""
+    from oracle.spamm_numpy import OracleModel
+    from spamm_b200.plan import ModelPlan
+    from spamm_b200.Spectrum import Spectrum
+    rng = np.random.RandomState(17)
+    comps = ["PL", "FE", "HOST", "BC"]
+    grids = (np.linspace(1200., 3300., 640), np.linspace(3800., 9000., 1002), np.linspace(3600., 3700., 64),
+             np.linspace(3000., 4200., 450), np.linspace(3640., 5200., 1090), np.linspace(1500., 3650., 700),
+             1000.0 + np.arange(18000) * 0.5)
+    lo = np.array([0, -3, 0, 0, 0, 901, 0, 0, 0, 0, 0, 0, 0, 30, 0, 500, 0, -10, 100, 2], dtype=float)
+    hi = np.array([1e-13, 3, 1e-13, 1e-13, 1e-13, 1e4, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e-14, 1e3,
+                   1e-13, 1e5, 2, 10, 1e4, 9], dtype=float)
+    for wl in grids:
+        o0 = OracleModel(wl, wl, wl, comps=comps)
+        fl = [o0.component_flux(cn, TRUTH[cn]) for cn in comps]
+        d = np.sum(fl, axis=0) * (1 + 0.01 * rng.standard_normal(len(wl)))
+        e = 0.05 * np.abs(d) + 1e-18
+        n = 6 if len(wl) > 5000 else 14
+        params = lo + (hi - lo) * rng.rand(n, 20)
+        params[1, 15] = 600.0                        # cold: large h nu / kT
+        params[2, 19] = 8.7                          # SH95 table off its density clamp
+        o = OracleModel(wl, d, e, comps=comps)
+        o.set_bounds(lo, hi)
+        with np.errstate(all="ignore"):
+            want = o.ln_posterior_batch(params)
+        sp = Spectrum(wl, d, e)
+
+        def plan_for():
+            cs = _components(comps)
+            for cc in cs:
+                cc.initialize(sp)
+            return ModelPlan(cs, sp, with_priors=False, bounds=(lo, hi), max_walkers=16)
+        full = plan_for()
+        assert full.specialised
+        got = full.lnposterior_host(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL, (len(wl), wl[0], got, want)
+        monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+        gplan = plan_for()
+        assert not gplan.specialised
+        gen = gplan.lnposterior_host(params)
+        monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
+        assert rel_err(got, gen).max() < 1e-12, (len(wl), wl[0])
+        for split in (0, 2, 4, 8):
+            full.set_walker_split(split)
+            assert np.array_equal(full.lnposterior_host(params), got), (len(wl), split)
+        assert full.status() == 0
