@@ -638,7 +638,12 @@ constexpr int kChunk = 32 * kPix;      // pixels per warp task
 // both parts on, Lorentzian lines, far-field series, bank rows): every component test, template count
 // and line-type branch below folds away, which roughly halves the non-FP64 instructions of a task.
 constexpr int kFullFe = 3, kFullHost = 7, kFullClusters = 4, kFullSuper = 3;
-template <int MODE, bool CANON, bool SPLIT, bool FULL>
+// SPEC = 0: generic.  Otherwise a bit set of the components the instantiation is compiled for (NC is
+// always bit 0; kSpecFe: Fe x3, kSpecHost: host x7, kSpecBalmer: BalmerCombined with both parts on,
+// Lorentzian + series, kSpecExt: a trailing Extinction); the supported sets are listed in kSpecs.
+constexpr int kSpecNc = 1, kSpecFe = 2, kSpecHost = 4, kSpecBalmer = 8, kSpecExt = 16;
+constexpr int kSpecs[] = {1, 3, 5, 9, 15, 31};    // NC | NC+Fe | NC+host | NC+Balmer | full | full+Extinction
+template <int MODE, bool CANON, bool SPLIT, int SPEC>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
           uint32_t mask, DirectRows dr, PeerOut po) {
@@ -691,16 +696,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     // Extinction is the last component (run_spamm.py:123-125) and multiplies the flux summed so far
     // (Model.py:358-361, 384-395); selected alone (component flux API) it returns the curve itself
-    const bool has_ext = !FULL && pl.ext_k != nullptr && ((mask >> pl.ext_q) & 1u);
+    constexpr bool FULL = SPEC != 0;
+    constexpr int NFE = (SPEC & kSpecFe) ? kFullFe : 0, NHOST = (SPEC & kSpecHost) ? kFullHost : 0;
+    const bool has_ext = FULL ? (SPEC & kSpecExt) != 0 : pl.ext_k != nullptr && ((mask >> pl.ext_q) & 1u);
     const bool ext_alone = has_ext && (mask & ~(1u << pl.ext_q)) == 0u;
-    if (FULL) { has_fe = true; has_host = true; }
+    if (FULL) { has_fe = NFE > 0; has_host = NHOST > 0; }
     const bool has_nc = FULL ? true : off_nc >= 0;
     const bool nc_broken = FULL ? false : pl.nc_broken != 0;
-    const bool have_balmer = FULL ? true : off_bal >= 0;
-    const int n_fe = FULL ? kFullFe : (has_fe ? pl.fe.n_templ : 0);
-    const int n_host = FULL ? kFullHost : (has_host ? pl.host.n_templ : 0);
-    const bool do_bc = FULL ? true : have_balmer && pl.bc_on;
-    const bool do_bpc = FULL ? true : have_balmer && pl.bpc_on;
+    const bool have_balmer = FULL ? (SPEC & kSpecBalmer) != 0 : off_bal >= 0;
+    const int n_fe = FULL ? NFE : (has_fe ? pl.fe.n_templ : 0);
+    const int n_host = FULL ? NHOST : (has_host ? pl.host.n_templ : 0);
+    const bool do_bc = FULL ? have_balmer : have_balmer && pl.bc_on;
+    const bool do_bpc = FULL ? have_balmer : have_balmer && pl.bpc_on;
     const bool lorentz = FULL ? true : pl.line_type == SPAMM_LINE_LORENTZIAN;
     const bool series_on = FULL ? true : pl.series_on != 0;
     constexpr bool PAIR = FULL && kPix == 2;      // adjacent-pixel lanes with 16-byte loads
@@ -977,7 +984,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         {
             double fe_v[kPix], host_v[kPix], nc_v[kPix];
             if (FULL) {
-                templ_sum_2<kFullFe, kFullHost, PAIR>(c.tc, i0, fe_v, host_v);
+                if constexpr (NFE + NHOST > 0) templ_sum_2<NFE, NHOST, PAIR>(c.tc, i0, fe_v, host_v);
             } else {
                 if (n_fe) templ_sum(c, 0, n_fe, i0, fe_v);
                 if (n_host) templ_sum(c, n_fe, n_host, i0, host_v);
@@ -1102,7 +1109,13 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
             if (!CANON && q_bal + 1 < pl.n_comp) v = v + post[q];
             if (has_ext) {
-                const double e = pow(10.0, (-0.4 * c.p[pl.ext_off]) * pl.ext_k[i]);   // ReddeningLaw.py:19,45,71,97,122
+                // pow(10, -0.4 * E(B-V) * k) (ReddeningLaw.py:19,45,71,97,122) as exp(y ln 10) with the
+                // product carried in double-double: ~1 ulp, a fifth of the cost of pow()
+                const double y = (-0.4 * c.p[pl.ext_off]) * pl.ext_k[i];
+                const double th = y * 2.302585092994046;
+                const double tl = fma(y, 2.302585092994046, -th) + y * (-2.1707562233822494e-16);
+                double e = exp_fast<!FULL>(th);
+                e = fma(e, tl, e);
                 v = (ext_alone ? 1.0 : v) * e;
             }
             const bool live = i < P;
@@ -1714,8 +1727,7 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     // Te_min; tau_BE (wl/edge)^3 over the staged pixels.
     pd.exp_safe = 0;
     pd.nc_pair_ok = 0;
-    if (d->prior_lo && d->prior_hi && seen[SPAMM_COMP_NUCLEAR] && seen[SPAMM_COMP_BALMER] && !d->nc_broken_pl &&
-        pd.bc_on) {
+    if (d->prior_lo && d->prior_hi && seen[SPAMM_COMP_NUCLEAR] && !d->nc_broken_pl) {
         int o_nc = -1, o_bal = -1;
         for (int q = 0; q < pd.n_comp; ++q) {
             if (pd.comp_kind[q] == SPAMM_COMP_NUCLEAR) o_nc = pd.comp_off[q];
@@ -1724,13 +1736,21 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         double lmax = 0.0;
         for (int i = 0; i < P; ++i) lmax = std::max(lmax, std::fabs(std::log(d->wl[i] / d->nc_norm_wl)));
         const double smax = std::max(std::fabs(d->prior_lo[o_nc + 1]), std::fabs(d->prior_hi[o_nc + 1]));
-        const double te_lo = d->prior_lo[o_bal + 1];
-        const double taumax = std::max(std::fabs(d->prior_lo[o_bal + 2]), std::fabs(d->prior_hi[o_bal + 2]));
-        const double hnu0 = d->h_cgs * (d->c_aa / d->wl[0]);
-        const double t3max = std::pow(d->wl[std::max(pd.bc_nstage, 1) - 1] / d->balmer_edge, 3.0);
-        const bool ok = smax * lmax < 690.0 && te_lo > 0.0 && hnu0 / (d->kb_cgs * te_lo) < 690.0 &&
-                        taumax * t3max < 690.0;
-        pd.exp_safe = ok ? 1 : 0;    // NaN bounds compare false
+        bool ok = smax * lmax < 690.0;                                  // NaN bounds compare false
+        if (o_bal >= 0 && pd.bc_on) {
+            const double te_lo = d->prior_lo[o_bal + 1];
+            const double taumax = std::max(std::fabs(d->prior_lo[o_bal + 2]), std::fabs(d->prior_hi[o_bal + 2]));
+            const double hnu0 = d->h_cgs * (d->c_aa / d->wl[0]);
+            const double t3max = std::pow(d->wl[std::max(pd.bc_nstage, 1) - 1] / d->balmer_edge, 3.0);
+            ok = ok && te_lo > 0.0 && hnu0 / (d->kb_cgs * te_lo) < 690.0 && taumax * t3max < 690.0;
+        }
+        if (seen[SPAMM_COMP_EXTINCTION]) {
+            double kmax = 0.0;
+            for (int i = 0; i < P; ++i) kmax = std::max(kmax, std::fabs(d->ext_k[i]));
+            const double emax = std::max(std::fabs(d->prior_lo[pd.ext_off]), std::fabs(d->prior_hi[pd.ext_off]));
+            ok = ok && 0.4 * emax * kmax * 2.302585092994046 < 690.0;
+        }
+        pd.exp_safe = ok ? 1 : 0;
         double dmax = 0.0;
         for (int i = 0; i + 1 < P; ++i) dmax = std::max(dmax, std::fabs(std::log(d->wl[i + 1] / d->wl[i])));
         pd.nc_pair_ok = (P % 2 == 0 && smax * dmax <= 0.016) ? 1 : 0;
@@ -1741,16 +1761,19 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
     const int sb = (int)pl->smem_bytes;
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<1, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-    CUDA_TRY(cudaFuncSetAttribute(k_walkers<0, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+#define SPAMM_SMEM_ATTR(...) \
+    CUDA_TRY(cudaFuncSetAttribute(k_walkers<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb))
+    SPAMM_SMEM_ATTR(0, true, false, 0); SPAMM_SMEM_ATTR(1, true, false, 0);
+    SPAMM_SMEM_ATTR(0, false, false, 0); SPAMM_SMEM_ATTR(1, false, false, 0);
+    SPAMM_SMEM_ATTR(0, true, true, 0); SPAMM_SMEM_ATTR(1, true, true, 0);
+    SPAMM_SMEM_ATTR(0, false, true, 0); SPAMM_SMEM_ATTR(1, false, true, 0);
+    SPAMM_SMEM_ATTR(0, true, false, 1); SPAMM_SMEM_ATTR(0, true, true, 1);
+    SPAMM_SMEM_ATTR(0, true, false, 3); SPAMM_SMEM_ATTR(0, true, true, 3);
+    SPAMM_SMEM_ATTR(0, true, false, 5); SPAMM_SMEM_ATTR(0, true, true, 5);
+    SPAMM_SMEM_ATTR(0, true, false, 9); SPAMM_SMEM_ATTR(0, true, true, 9);
+    SPAMM_SMEM_ATTR(0, true, false, 15); SPAMM_SMEM_ATTR(0, true, true, 15);
+    SPAMM_SMEM_ATTR(0, true, false, 31); SPAMM_SMEM_ATTR(0, true, true, 31);
+#undef SPAMM_SMEM_ATTR
     CUDA_TRY(cudaDeviceSynchronize());
     return SPAMM_OK;
 }
@@ -1842,7 +1865,7 @@ static bool canonical_order(const PlanDev& pd, uint32_t mask) {
 
 // One launch of the fused kernel.  Ensembles too small to fill the GPU (fewer walkers than
 // resident CTA slots) run one walker per thread-block cluster of 2/4/8 CTAs (SPLIT instantiation).
-template <int MODE, bool CANON, bool SPLIT, bool FULL = false>
+template <int MODE, bool CANON, bool SPLIT, int SPEC = 0>
 static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
                       const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                       PeerOut po) {
@@ -1857,7 +1880,7 @@ static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, 
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     if (SPLIT) { cfg.attrs = &attr; cfg.numAttrs = 1; }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, FULL>, pd, params_dev, w0, out_dev, mask, dr, po));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, SPEC>, pd, params_dev, w0, out_dev, mask, dr, po));
     return SPAMM_OK;
 }
 
@@ -1870,21 +1893,33 @@ static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
     return c;
 }
 
-// the headline model the FULL instantiation is compiled for
-static bool full_model(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, const DirectRows& dr) {
-    if (!pl->use_full_kernel || pd.n_comp != 4 || mask != 0xFu || dr.fe_f || dr.host_f) return false;
-    return pd.comp_kind[0] == SPAMM_COMP_NUCLEAR && pd.comp_kind[1] == SPAMM_COMP_FE &&
-           pd.comp_kind[2] == SPAMM_COMP_HOST && pd.comp_kind[3] == SPAMM_COMP_BALMER && !pd.nc_broken &&
-           pd.fe.n_templ == kFullFe && pd.host.n_templ == kFullHost && pd.bc_on && pd.bpc_on &&
-           pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on && pd.exp_safe && pd.lo != nullptr &&
-           pd.n_clusters == kFullClusters && pd.n_super == kFullSuper && pd.nc_pair_ok;
+// Which specialised instantiation (SPEC bit set, 0 = none) serves ln-posterior calls on this plan
+static int spec_of(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, const DirectRows& dr) {
+    if (!pl->use_full_kernel || mask != (1u << pd.n_comp) - 1u || dr.fe_f || dr.host_f) return 0;
+    if (!pd.exp_safe || !pd.nc_pair_ok || pd.lo == nullptr || pd.nc_broken) return 0;
+    int spec = 0, last = -1;
+    for (int q = 0; q < pd.n_comp; ++q) {
+        const int kind = pd.comp_kind[q];
+        if (kind <= last) return 0;                       // run_spamm's order only
+        last = kind;
+        if (kind == SPAMM_COMP_NUCLEAR) spec |= kSpecNc;
+        else if (kind == SPAMM_COMP_FE) { if (pd.fe.n_templ != kFullFe) return 0; spec |= kSpecFe; }
+        else if (kind == SPAMM_COMP_HOST) { if (pd.host.n_templ != kFullHost) return 0; spec |= kSpecHost; }
+        else if (kind == SPAMM_COMP_BALMER) {
+            if (!(pd.bc_on && pd.bpc_on && pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on &&
+                  pd.n_clusters == kFullClusters && pd.n_super == kFullSuper)) return 0;
+            spec |= kSpecBalmer;
+        } else if (kind == SPAMM_COMP_EXTINCTION) spec |= kSpecExt;
+    }
+    for (int k : kSpecs) if (k == spec) return spec;
+    return 0;
 }
 
 extern "C" int spamm_plan_specialised(const SpammPlan* pl) {
     if (!pl) return SPAMM_EINVAL;
     DirectRows none{nullptr, nullptr, nullptr, nullptr};
     const bool bank = pl->template_mode != SPAMM_TEMPLATES_DIRECT;
-    return bank && full_model(pl, pl->dev, (1u << pl->dev.n_comp) - 1u, none) ? 1 : 0;
+    return bank && spec_of(pl, pl->dev, (1u << pl->dev.n_comp) - 1u, none) != 0 ? 1 : 0;
 }
 
 template <int MODE>
@@ -1892,9 +1927,17 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                     PeerOut po) {
     const int c = cluster_size_for(pl, n_walkers);
-    if (MODE == 0 && full_model(pl, pd, mask, dr)) {
-        if (c > 1) return launch_one<0, true, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po);
-        return launch_one<0, true, false, true>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+    if (MODE == 0) {
+#define SPAMM_LAUNCH_SPEC(S)                                                                                     \
+    case S:                                                                                                      \
+        return c > 1 ? launch_one<0, true, true, S>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po) \
+                     : launch_one<0, true, false, S>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        switch (spec_of(pl, pd, mask, dr)) {
+            SPAMM_LAUNCH_SPEC(1) SPAMM_LAUNCH_SPEC(3) SPAMM_LAUNCH_SPEC(5) SPAMM_LAUNCH_SPEC(9)
+            SPAMM_LAUNCH_SPEC(15) SPAMM_LAUNCH_SPEC(31)
+            default: break;
+        }
+#undef SPAMM_LAUNCH_SPEC
     }
     if (c > 1) {
         return canon ? launch_one<MODE, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po)

@@ -556,3 +556,51 @@ def test_specialised_kernel_on_awkward_grids(monkeypatch):
             full.set_walker_split(split)
             assert np.array_equal(full.lnposterior_host(params), got), (len(wl), split)
         assert full.status() == 0
+
+
+@pytest.mark.parametrize("name", ["cfg2_nc_fe", "cfg3_nc_hg", "cfg4_nc_bc", "cfg5_full"])
+def test_specialised_instantiations_of_the_baseline_configs(name, monkeypatch):
+    """BASELINE configs 2-5 each run their own compile-time specialised instantiation (NC+Fe, NC+host,
+    NC+Balmer, full); each must agree with the generic instantiation to a few ulp, with the fixture,
+    and be independent of the walker split."""
+    z, _ = lnpost_cases()
+    c = Case(z, name)
+    m = _model(c)
+    assert m.plan.specialised
+    got = m.lnposterior_batch(c.params)
+    assert rel_err(got, c.lnpost).max() < LNPOST_RTOL
+    monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+    g = _model(c)
+    assert not g.plan.specialised
+    ref = g.lnposterior_batch(c.params)
+    monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
+    assert rel_err(got, ref).max() < 1e-13
+    for split in (2, 4, 8):
+        m.plan.set_walker_split(split)
+        assert np.array_equal(m.lnposterior_batch(c.params), got)
+
+
+def test_specialised_extinction_model(monkeypatch):
+    """full model + trailing Extinction: specialised instantiation (exp-based extinction factor) vs the
+    generic one and the reference fixture."""
+    from spamm_b200.Model import Model
+    from spamm_b200.Spectrum import Spectrum
+    from spamm_b200.components.ReddeningLaw import Extinction
+    z = np.load(os.path.join(GOLDEN, "extinction.npz"))
+    g = lambda k: z["model/full_mw/%s" % k]  # noqa: E731
+
+    def build():
+        m = Model()
+        m.components += _components([str(c) for c in g("comps")])
+        m.components.append(Extinction(MW=True))
+        m.data_spectrum = Spectrum(g("wl"), g("flux"), g("err"))
+        return m
+    m = build()
+    got = m.lnposterior_batch(g("params"))
+    assert m.plan.specialised
+    assert rel_err(got, g("lnpost")).max() < LNPOST_RTOL
+    monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+    m2 = build()
+    ref = m2.lnposterior_batch(g("params"))
+    assert not m2.plan.specialised
+    assert rel_err(got, ref).max() < 1e-13

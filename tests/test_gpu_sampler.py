@@ -104,7 +104,11 @@ def test_spamm_driver_pickle_and_samples(tmp_path):
     _, samples, _, _ = get_samples([res["pickle"], res], burn=100)
     assert samples.shape == (2 * 32 * 1400, 2)
     with pytest.raises(ValueError):
-        spamm(["PL", "MW_EXT"], (z["wl"], z["flux"], z["err"]), save=False)
+        spamm(["PL", "BROADLINE"], (z["wl"], z["flux"], z["err"]), save=False)
+    # the *_EXT flags append an Extinction component (run_spamm.py:123-125 as intended)
+    ext = spamm(["PL", "MW_EXT"], (z["wl"], z["flux"], z["err"]), n_walkers=32, n_iterations=20, save=False, seed=3)
+    assert [c.name for c in ext["model"].components] == ["Nuclear", "Extinction"]
+    assert ext["model"].sampler.chain.shape == (32, 20, 3)
 
 
 def test_device_sampler_matches_emcee_restatement_on_full_model():
