@@ -1888,7 +1888,7 @@ static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
     if (pl->split_mode == 0) return 1;
     int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
     int c = 1;
-    while (c < 8 && n_walkers * c * 2 <= slots) c *= 2;
+    while (c < 8 && n_walkers * c * 4 <= slots) c *= 2;       // keep the split grid within half the slots
     if (pl->split_mode > 1) c = pl->split_mode;          // forced (tests)
     return c;
 }
