@@ -212,6 +212,17 @@ int spamm_chain_record(const double* walkers_dev, const double* lnp_dev, int32_t
                        int32_t n_dim, int64_t iter, int64_t n_iter, double* chain_dev,
                        double* lnp_chain_dev, void* stream);
 
+/* n_iter whole iterations of the stretch move on one device -- for each iteration both half-steps
+ * (propose, spamm_lnpost_batch on the proposals, accept) and, if chain_dev/lnp_chain_dev are not
+ * NULL, the chain record at [walker][iter0 + i][*] of a chain of length chain_len -- queued on
+ * `stream` in one call.  This is the loop of emcee's EnsembleSampler.sample() (call site
+ * Model.py:283-289) without a round trip to the host language per half-step.  q_dev [K/2][D],
+ * z_dev [K/2], lnp_q_dev [K/2] are caller-owned scratch. */
+int spamm_stretch_run(SpammPlan* plan, double* walkers_dev, double* lnp_dev, int32_t n_walkers, double a,
+                      uint64_t seed, uint64_t iter0, int32_t n_iter, double* q_dev, double* z_dev,
+                      double* lnp_q_dev, int64_t* naccepted_dev, double* chain_dev, double* lnp_chain_dev,
+                      int64_t chain_len, void* stream);
+
 /* FP64 FMA throughput probe (roofline denominator: MEASURED_PEAKS.json has no
  * FP64 entry).  Runs `iters` dependent-chain DFMA iterations on every SM and
  * returns the achieved TFLOP/s (2 flop per FMA) measured with CUDA events. */

@@ -84,7 +84,7 @@ EXPORTS = [
     "spamm_plan_create", "spamm_plan_destroy", "spamm_lnpost_batch", "spamm_lnpost_batch_host", "spamm_lnpost_batch_p2p",
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
     "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split", "spamm_plan_specialised",
-    "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record",
+    "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record", "spamm_stretch_run",
     "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version",
 ]
 
@@ -138,6 +138,8 @@ def load():
     lib.spamm_stretch_accept.restype = ctypes.c_int
     lib.spamm_chain_record.argtypes = [vp, vp, i32, i32, i64, i64, vp, vp, vp]
     lib.spamm_chain_record.restype = ctypes.c_int
+    lib.spamm_stretch_run.argtypes = [vp, vp, vp, i32, dbl, u64, u64, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.spamm_stretch_run.restype = ctypes.c_int
     lib.spamm_fp64_peak_probe.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.spamm_fp64_peak_probe.restype = ctypes.c_int
     lib.spamm_last_error.argtypes = []

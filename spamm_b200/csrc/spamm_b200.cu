@@ -2132,6 +2132,39 @@ extern "C" int spamm_chain_record(const double* walkers_dev, const double* lnp_d
     return SPAMM_OK;
 }
 
+// n_iter full iterations of the stretch move (both half-steps, optional chain record) queued on
+// `stream` without returning to the host language in between
+extern "C" int spamm_stretch_run(SpammPlan* pl, double* walkers_dev, double* lnp_dev, int32_t K, double a,
+                                 uint64_t seed, uint64_t iter0, int32_t n_iter, double* q_dev, double* z_dev,
+                                 double* lnp_q_dev, int64_t* naccepted_dev, double* chain_dev,
+                                 double* lnp_chain_dev, int64_t chain_len, void* stream) {
+    if (!pl || !walkers_dev || !lnp_dev || !q_dev || !z_dev || !lnp_q_dev)
+        return set_error(SPAMM_EINVAL, "null argument");
+    if (K < 2 || (K & 1) || n_iter < 0) return set_error(SPAMM_EINVAL, "need an even walker count");
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    if ((chain_dev || lnp_chain_dev) && (int64_t)iter0 + n_iter > chain_len)
+        return set_error(SPAMM_EINVAL, "chain buffer too short");
+    const int D = pl->dev.D;
+    for (int it = 0; it < n_iter; ++it) {
+        const uint64_t iteration = iter0 + (uint64_t)it;
+        for (int half = 0; half < 2; ++half) {
+            int rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream);
+            if (rc) return rc;
+            if ((rc = launch_walkers<0>(pl, full_mask(pl), q_dev, K / 2, lnp_q_dev, (cudaStream_t)stream, false)))
+                return rc;
+            if ((rc = spamm_stretch_accept(walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed,
+                                           iteration, naccepted_dev, stream)))
+                return rc;
+        }
+        if (chain_dev || lnp_chain_dev) {
+            int rc = spamm_chain_record(walkers_dev, lnp_dev, K, D, (int64_t)iteration, chain_len, chain_dev,
+                                        lnp_chain_dev, stream);
+            if (rc) return rc;
+        }
+    }
+    return SPAMM_OK;
+}
+
 extern "C" int spamm_fp64_peak_probe(int32_t iters, int32_t repeats, double* tflops_out) {
     if (!tflops_out || iters < 1 || repeats < 1) return set_error(SPAMM_EINVAL, "bad argument");
     int dev_id = 0;

@@ -76,6 +76,7 @@ class EnsembleSampler(object):
         self.lib = _lib.load()
         self.seed = int(np.random.randint(0, 2 ** 31 - 1) if seed is None else seed)
         self.store_chain = store_chain
+        self.native_loop = True          # single device: iterate inside the library (spamm_stretch_run)
         self.iterations = 0
         self._chain = None
         self._lnprob = None
@@ -194,15 +195,31 @@ class EnsembleSampler(object):
                 lnprob[:, :start] = self._lnprob[:, :start]
             self._chain, self._lnprob = chain, lnprob
         vp = ctypes.c_void_p
-        for it in range(start, total):
-            self.half_step(0, it)
-            self.half_step(1, it)
-            if self.store_chain:
-                _lib.check(self.lib.spamm_chain_record(vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()),
-                                                       self.k, self.dim, it, total,
-                                                       vp(self._chain.data_ptr()), vp(self._lnprob.data_ptr()),
-                                                       self._stream()))
-            self.iterations += 1
+        if self.exchange == "single" and self.native_loop:
+            # one device: the whole loop runs inside the library (spamm_stretch_run), a few hundred
+            # iterations per call so a long run does not queue unboundedly far ahead of the device
+            lnp_q = torch.empty(self.k // 2, dtype=torch.float64, device=dev)
+            it = start
+            while it < total:
+                n = min(256, total - it)
+                _lib.check(self.lib.spamm_stretch_run(
+                    self.plan._h, vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()), self.k, self.a,
+                    self.seed, it, n, vp(self._q.data_ptr()), vp(self._z.data_ptr()), vp(lnp_q.data_ptr()),
+                    vp(self._nacc.data_ptr()),
+                    vp(self._chain.data_ptr()) if self.store_chain else None,
+                    vp(self._lnprob.data_ptr()) if self.store_chain else None, total, self._stream()))
+                it += n
+                self.iterations += n
+        else:
+            for it in range(start, total):
+                self.half_step(0, it)
+                self.half_step(1, it)
+                if self.store_chain:
+                    _lib.check(self.lib.spamm_chain_record(vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()),
+                                                           self.k, self.dim, it, total,
+                                                           vp(self._chain.data_ptr()), vp(self._lnprob.data_ptr()),
+                                                           self._stream()))
+                self.iterations += 1
         torch.cuda.synchronize()
         pos = self._walkers.cpu().numpy()
         lnp = self._lnp.cpu().numpy()

@@ -148,3 +148,23 @@ def test_device_sampler_matches_emcee_restatement_on_full_model():
     assert abs(s.acceptance_fraction.mean() - acc_ref.mean()) < 0.05
     # both recover the truth of the synthetic spectrum (err = 5 %, no noise)
     assert np.all(np.abs(ma[:, 0] - truth) < 5 * width + 1e-30)
+
+
+def test_native_loop_equals_python_loop():
+    """spamm_stretch_run (the whole iteration loop inside the library) produces the same chain, bit for
+    bit, as the per-half-step calls driven from Python, including a continued run."""
+    from spamm_b200.sampler import EnsembleSampler
+    from spamm_b200.Model import ln_posterior
+    from spamm_b200.synth import full_model_workload
+    model, params = full_model_workload(n_pix=1024, n_walkers=64, seed=5)
+    chains = []
+    for native in (True, False):
+        s = EnsembleSampler(nwalkers=64, dim=20, lnpostfn=ln_posterior, args=[model], seed=11)
+        s.native_loop = native
+        pos, lnp, _ = s.run_mcmc(params, 300)          # more than one 256-iteration library call
+        s.run_mcmc(pos, 20, lnprob0=lnp)
+        assert s.chain.shape == (64, 320, 20)
+        chains.append((s.chain, s.lnprobability, s.naccepted))
+    for a, b in zip(*chains):
+        assert np.array_equal(a, b)
+    assert 0.05 < chains[0][2].mean() / 320 < 0.9
