@@ -617,9 +617,10 @@ __device__ __forceinline__ void cluster_series(const ClusterW& cw, int K, const 
 
 // number of series terms for rho^2 = As / Cmin  (rho^K <~ 1e-16; capped at kMom, which the
 // far test rho <= 0.1 makes sufficient)
-__device__ __forceinline__ int series_terms(double rho2) {
-    float l = -__logf((float)rho2);
-    int K = ((int)(74.0f / l) + 2) & ~1;          // even
+// (single precision throughout: K only has to be large enough, and the +2 absorbs the rounding)
+__device__ __forceinline__ int series_terms(double As, double cmin) {
+    float l = __logf((float)cmin) - __logf((float)As);          // -ln(rho^2) >= ln 100
+    int K = ((int)__fdividef(74.0f, l) + 2) & ~1;                 // even
     return min(max(K, 4), kMom);
 }
 
@@ -861,7 +862,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 w2 = wv * wv;
                 a = lorentz ? rr * wv : rr;
                 const double d = lam_e - sLine[gq * 12 + r4];
-                if (lorentz) s += a / (d * d + w2);
+                if (lorentz) s += FULL ? a * rcp_fast(fma(d, d, w2)) : a / (d * d + w2);
                 else s += a * exp_fast(-(d * d) / w2);
             }
             sLine[gq * 12 + 4 + r4] = w2;
@@ -1080,7 +1081,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                             g0 = pl.cl[kc].g_lo; g1 = pl.cl[kc].g_hi;
                         }
                     }
-                    if (series) cluster_series(c.cw[kc], series_terms(c.cw[kc].As / cmin), lam, acc);
+                    if (series) cluster_series(c.cw[kc], series_terms(c.cw[kc].As, cmin), lam, acc);
                     else lorentz_direct(sL2, g0, g1, lam, acc);
                 }
             } else {
