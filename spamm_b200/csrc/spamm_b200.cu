@@ -949,8 +949,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const int n_chunks = pl.n_chunks;
     const int n_groups = n_pad >> 2;
     const double2* sL2 = reinterpret_cast<const double2*>(sLine);
-    // (static round-robin: a shared task counter costs a dozen instructions per task, and the cost of a
-    // task varies smoothly with its position, so every warp gets the same mix)
+    // (static round-robin.  A shared task counter costs a dozen instructions per task -- ptxas turns even
+    // a plain atom.shared into its warp-aggregation sequence -- and measured 2.7 % slower, 1 % slower
+    // when tasks are fetched in pairs, although the one task inside the line forest, ~13x the work of
+    // the others, leaves its warp behind: the SM's other CTAs fill the gap.)
     for (int t = SPLIT ? warp * csize + crank : warp; t < n_chunks; t += (kThreads / 32) * csize) {
         const int chunk = n_chunks - 1 - t;
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
@@ -1063,6 +1065,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                         sup_cmin = fma(u, u, c.cw[sup].kcb2);
                     }
                     nseg = sup >= 0 ? 2 : 1 + n_base;
+                }
+                if (FULL && sup >= 0) {
+                    // the common case, straight-line: the 4/8/16 lines before the far superset, then its series
+                    lorentz_direct(sL2, 0, pl.cl[sup].g_lo, lam, acc);
+                    cluster_series(c.cw[sup], series_terms(c.cw[sup].As, sup_cmin), lam, acc);
+                    nseg = 0;
                 }
 #pragma unroll 1
                 for (int sg = 0; sg < nseg; ++sg) {
