@@ -377,7 +377,7 @@ def run_ours(args):
                     "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); "
                                    "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
                     "algorithmic_flops_per_eval": flops,
-                    "kernel": "k_walkers<0, true, false, true> (headline-model instantiation)",
+                    "kernel": "k_walkers<0, true, false, 15> (full-model instantiation)",
                     "note": "achieved = SURVEY 8(d) algorithmic flops x evals/s; the default kernel sums "
                             "distant Balmer-line clusters by a far-field series and executes ~8x fewer "
                             "flops than that count, so frac can exceed 1; exact_line_sum below is the "
