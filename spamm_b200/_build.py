@@ -30,7 +30,8 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [SRC, os.path.join(INC, "spamm_b200.h")]
+    csrc = os.path.dirname(SRC)
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(INC, "spamm_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

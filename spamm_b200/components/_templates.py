@@ -2,7 +2,7 @@
 N templates, Gaussian-broadened in ln-lambda space by a per-walker width and
 scaled (reference: FeComponent.py / HostGalaxyComponent.py are copy-paste
 twins).  The per-call arithmetic -- kernel, convolution, interpolation onto the
-data grid, normalisation -- runs on the GPU (csrc/spamm_b200.cu: k_conv_rows,
+data grid, normalisation -- runs on the GPU (csrc/template_kernels.cuh: k_conv_rows,
 k_interp_rows, k_norm_rows, k_walkers); this host class only prepares the
 ln-lambda grids once, as ``initialize`` does in the reference."""
 import numpy as np
