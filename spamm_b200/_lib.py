@@ -101,6 +101,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if "SPAMM_B200_LIB" not in os.environ and "SPAMM_B200_NO_AUTOBUILD" not in os.environ:
+        # in-tree library missing or older than its sources: compile it (nvcc, sm_100a) -- still no
+        # fallback of any other kind: if that fails, so does the import of the product path
+        from . import _build
+        try:
+            if _build.needs_build():
+                _build.build()
+        except Exception as exc:
+            if not os.path.exists(LIB_PATH):
+                raise SpammError("CUDA library %s is missing and could not be built: %s" % (LIB_PATH, exc))
     if not os.path.exists(LIB_PATH):
         raise SpammError(
             "CUDA library %s is missing: run `python -m spamm_b200._build` (needs nvcc). "
