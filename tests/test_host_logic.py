@@ -50,9 +50,10 @@ def test_ctypes_struct_matches_header_layout():
 #include <stddef.h>
 #include "spamm_b200.h"
 int main(void){
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(SpammTemplateSet), sizeof(SpammPlanDesc),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %d\n", sizeof(SpammTemplateSet), sizeof(SpammPlanDesc),
     offsetof(SpammPlanDesc, fe), offsetof(SpammPlanDesc, host), offsetof(SpammPlanDesc, template_mode),
-    offsetof(SpammPlanDesc, sh95_z), offsetof(SpammPlanDesc, max_walkers));
+    offsetof(SpammPlanDesc, sh95_z), offsetof(SpammPlanDesc, max_walkers), offsetof(SpammPlanDesc, ext_k),
+    SPAMM_ABI_VERSION, (int)SPAMM_COMP_EXTINCTION);
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as td:
@@ -64,7 +65,8 @@ int main(void){
     got = [ctypes.sizeof(_lib.SpammTemplateSet), ctypes.sizeof(_lib.SpammPlanDesc),
            _lib.SpammPlanDesc.fe.offset, _lib.SpammPlanDesc.host.offset,
            _lib.SpammPlanDesc.template_mode.offset, _lib.SpammPlanDesc.sh95_z.offset,
-           _lib.SpammPlanDesc.max_walkers.offset]
+           _lib.SpammPlanDesc.max_walkers.offset, _lib.SpammPlanDesc.ext_k.offset, _lib.ABI_VERSION,
+           _lib.COMP_EXTINCTION]
     assert [int(v) for v in out] == got
 
 
