@@ -409,7 +409,13 @@ def run_ours(args):
                                           params_host[:n_cpu], cores)
             gpu_vals = res[:n_cpu]
             rel = float(np.max(np.abs(vals - gpu_vals) / np.abs(vals)))
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            # one core, in process (SURVEY.md 8(d) asks for n = 1 and n = all cores)
+            _oracle_init(wl, np.asarray(model.data_spectrum.flux), np.asarray(model.data_spectrum.flux_error))
+            t0 = time.perf_counter()
+            for p1 in params_host[:24]:
+                _oracle_eval(p1)
+            v1 = 24.0 / (time.perf_counter() - t0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_one_core": v1,
                    "sample": "first %d walkers of the same ensemble, numpy port of the reference, "
                              "multiprocessing.Pool(%d).map" % (n_cpu, cores),
                    "max_rel_diff_vs_gpu": rel}
