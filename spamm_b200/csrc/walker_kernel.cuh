@@ -410,7 +410,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             c.nc_slope1 = c.p[off_nc + 2]; c.nc_slope2 = c.p[off_nc + 3];
         }
     }
-    if (has_fe && warp == 1 && lane < n_fe) {
+    constexpr int kNW = kThreads / 32;                      // warps of the CTA (roles below wrap around)
+    if (has_fe && warp == 1 % kNW && lane < n_fe) {
         const TemplDev& ts = pl.fe;
         int t = lane;
         double norm = c.p[ts.param_off + t];
@@ -429,7 +430,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         c.tc[t].f = f;
         c.tc[t].a = norm / nf;                                          // Fe:334
     }
-    if (has_host && warp == 2 && lane < n_host) {
+    if (has_host && warp == 2 % kNW && lane < n_host) {
         const TemplDev& ts = pl.host;
         int t = lane;
         double norm = c.p[ts.param_off + t];
@@ -448,7 +449,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         c.tc[n_fe + t].f = f;
         c.tc[n_fe + t].a = norm / nf;                                        // HG:339
     }
-    if (warp == 3 && lane == 0) {
+    if (warp == 3 % kNW && lane == 0) {
         c.bc_istar = -1;
         c.kT = kT; c.tauBE = b_tau;
         if (do_bc) {
@@ -462,7 +463,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             if (max(kk.y, kk.w) >= pl.bc_nstage) atomicOr(pl.status, kStatBcStage);
         }
     }
-    if (warp == 4 && lane == 0) {
+    if (warp == 4 % kNW && lane == 0) {
         c.bpc_istar = -1;
         if (do_bpc) {
             double edge_wl = pl.edge * (1 - b_loff / pl.c_kms);          // BC:374
@@ -515,7 +516,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // ---- P3: finish the line table; BC and BpC normalisers; cluster moments -------------------------
     const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
     double bpc_scale = 0.0;
-    if (do_bc && warp == 7 && lane == 0) {
+    if (do_bc && warp == kNW - 1 && lane == 0) {
         double fnorm = bc_conv_at(pl, sF0, bc_istar);                    // BC:444
         c.bc_scale = b_norm / fnorm;                                     // BC:446
         c.bc_finite = isfinite(c.bc_scale) ? 1 : 0;
@@ -550,9 +551,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         // the walker-independent power series in z = S_ref / kT (mom_G), so only the n <= 50 lines of
         // the cluster are visited.
         const int n_cl = series_on && lorentz ? n_base + n_super : 0;
-        if (warp < n_cl) {
-            const ClusterDev& cd = pl.cl[warp];
-            const double* dd = pl.line_d[warp];
+        for (int kcl = warp; kcl < n_cl; kcl += kNW) {
+            const ClusterDev& cd = pl.cl[kcl];
+            const double* dd = pl.line_d[kcl];
             const bool poly = FULL && pl.mom_poly;
             const int n_end = poly ? min(cd.g_hi * 4, n50) : cd.g_hi * 4;
             double mk[kMom];
@@ -581,7 +582,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
             mk[0] += __shfl_xor_sync(0xffffffffu, mk[0], 1);
             if (poly) {
-                const double* G = pl.mom_G[warp] + (lane >> 1) * kMomPoly;
+                const double* G = pl.mom_G[kcl] + (lane >> 1) * kMomPoly;
                 double g[kMomPoly];
 #pragma unroll
                 for (int q = 0; q < kMomPoly; ++q) g[q] = G[q];
@@ -592,12 +593,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
                 mk[0] = fma(r50 * (width * (1.0 - shift)), acc, mk[0]);
             }
-            if (!(lane & 1)) c.cw[warp].mom[lane >> 1] = mk[0];
+            if (!(lane & 1)) c.cw[kcl].mom[lane >> 1] = mk[0];
             if (lane == 0) {
                 const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
                 const double kappa = width * width;
                 const double cb = cd.cb0 - shift * cd.cb0, R = cd.R0 - shift * cd.R0;
-                ClusterW& cw = c.cw[warp];
+                ClusterW& cw = c.cw[kcl];
                 cw.cb = cb;
                 cw.kcb2 = kappa * cb * cb;
                 cw.twoR = 2.0 * R;
