@@ -139,6 +139,17 @@ class Model(object):
         self.model_spectrum.flux = self.model_flux_batch(np.asarray(params, dtype=np.float64)[None, :])[0]
         return self.model_spectrum.flux
 
+    def add_component(self, component, parameters):
+        """Add one component's flux to `model_spectrum.flux` (Model.py:368-380); the step-wise form of
+        `model_flux`, kept for callers that build the model spectrum themselves."""
+        component_flux = component.flux(spectrum=self.data_spectrum, parameters=parameters)
+        self.model_spectrum.flux = self.model_spectrum.flux + component_flux
+
+    def reddening(self, component, parameters):
+        """Multiply `model_spectrum.flux` by the component's extinction curve (Model.py:384-395)."""
+        extinction = component.extinction(spectrum=self.data_spectrum, params=parameters)
+        self.model_spectrum.flux = np.array(self.model_spectrum.flux) * extinction
+
     def likelihood(self, model_spectrum_flux):
         """ln L of a model flux on the data grid (Model.py:418-445)."""
         import torch

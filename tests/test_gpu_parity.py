@@ -180,6 +180,13 @@ def test_model_api_pieces_agree():
             f = m.model_flux(c.params[i])
             v = m.likelihood(f) + lp
             assert abs(v - got[i]) <= 1e-12 * abs(got[i])
+            # the step-wise form of model_flux (Model.add_component, Model.py:368-380)
+            m.model_spectrum.flux = np.zeros(len(c.wl))
+            p = np.copy(c.params[i])
+            for comp in m.components:
+                m.add_component(component=comp, parameters=p[0:comp.parameter_count])
+                p = p[comp.parameter_count:]
+            assert np.max(np.abs(m.model_spectrum.flux - f)) <= 1e-13 * np.max(np.abs(f))
 
 
 def test_full_size_properties():
@@ -498,6 +505,14 @@ def test_extinction_component_vs_reference_golden():
         # the prior, component by component, through the reference-shaped host API
         p = g("params")[0]
         assert np.isfinite(m.prior(p)) == np.isfinite(g("lnpost")[0])
+        # the reference's own loop (Model.py:353-364): add_component for each flux, reddening for Extinction
+        m.model_spectrum.flux = np.zeros(len(g("wl")))
+        q = np.copy(p)
+        for comp in m.components:
+            step = m.reddening if comp.name == "Extinction" else m.add_component
+            step(component=comp, parameters=q[0:comp.parameter_count])
+            q = q[comp.parameter_count:]
+        assert np.max(np.abs(m.model_spectrum.flux - g("model_flux")[0])) <= FLUX_RTOL * np.max(np.abs(g("model_flux")[0]))
     # Extinction anywhere but last is rejected
     bad = Model()
     bad.components += [Extinction(MW=True)] + _components(["PL"])
