@@ -362,6 +362,43 @@ def run_ours(args):
         a, b = lnp.cpu().numpy(), lnp2.cpu().numpy()
         exact_rel = float(np.max(np.abs(a - b) / np.abs(b)))
 
+    # secondary figures of SURVEY.md 8(d): one stretch half-step (W/2 walkers per call) and the whole
+    # device sampler (walkers x iterations per second, proposals + ln-posterior + accept + chain record)
+    secondary = None
+    if world == 1 and not args.no_sampler:
+        from spamm_b200.sampler import EnsembleSampler
+        from spamm_b200.Model import ln_posterior
+        half = params[: n_local // 2].contiguous()
+        lnp_h = torch.empty(len(half), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            plan.lnposterior(half, out=lnp_h)
+        torch.cuda.synchronize()
+        evh = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for e0, e1 in evh:
+            flush.zero_()
+            e0.record()
+            plan.lnposterior(half, out=lnp_h)
+            e1.record()
+        torch.cuda.synchronize()
+        half_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evh]))
+        n_it = 40
+        for _ in range(2):         # the first pass pays the one-off device allocations of the chain buffers
+            smp = EnsembleSampler(nwalkers=n_local, dim=plan.n_dim, lnpostfn=ln_posterior, args=[model], seed=7,
+                                  store_chain=True)
+            smp.run_mcmc(params_host, 5)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            smp.run_mcmc(smp._walkers.cpu().numpy(), n_it)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        secondary = {"half_step": {"walkers": int(len(half)), "ms": half_ms,
+                                   "evals_per_s": len(half) / (half_ms * 1e-3)},
+                     "sampler": {"walkers": int(n_local), "iterations": n_it, "ms_per_iteration": 1e3 * dt / n_it,
+                                 "walker_steps_per_s": n_local * n_it / dt,
+                                 "acceptance_fraction": float(smp.acceptance_fraction.mean()),
+                                 "what": "emcee 2.2.1 stretch move on the device (spamm_stretch_run): propose, "
+                                         "ln-posterior, accept for both halves, chain record; wall clock"}}
+
     line = None
     if rank == 0:
         wl = np.asarray(model.data_spectrum.spectral_axis)
@@ -432,6 +469,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(n_local * 8), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "ms_per_step_minmax": [float(ms.min()), float(ms.max())],
+            "secondary": secondary,
         }
         print(json.dumps(line))
     if world > 1:
@@ -450,6 +488,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the half-step / device-sampler figures")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: how per-walker ln-probs reach every rank")
     args = ap.parse_args()
