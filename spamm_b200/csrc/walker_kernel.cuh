@@ -769,7 +769,33 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                     else lorentz_direct(sL2, g0, g1, lam, acc);
                 }
             } else {
-                for (int n = 0; n < n_lines; ++n) {
+                // Gaussian profile exp(-(d / w)^2), w_n = width * c_n (BC:316-319): beyond 27.4 widths the
+                // argument is below -750 and exp() is exactly 0.0 in the reference too, so only the lines
+                // with a centre in (lam_lo / (1 + 27.4 width), lam_hi / (1 - 27.4 width)) are visited --
+                // bit-identical to the full sum.  Centres fall with the line index.
+                int n_first = 0, n_last = n_lines;
+                {
+                    const double kw = 27.4 * (b_lwid / pl.c_kms);
+                    const double lam_lo = pl.wl[chunk * kChunk];                         // live: chunk < n_chunks
+                    const double lam_hi = pl.wl[min(chunk * kChunk + kChunk, P) - 1];      // last live pixel
+                    const double c_min = lam_lo / (1.0 + kw) * (1.0 - 1e-12);
+                    const double c_max = kw < 1.0 ? lam_hi / (1.0 - kw) * (1.0 + 1e-12) : CUDART_INF;
+                    if (kw >= 0.0 && isfinite(lam_lo) && isfinite(lam_hi)) {
+                        int lo = 0, hi = n_lines;                 // first index with centre <= c_max
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sLine[(mid >> 2) * 12 + (mid & 3)] > c_max) lo = mid + 1; else hi = mid;
+                        }
+                        n_first = lo;
+                        hi = n_lines;                             // first index with centre < c_min
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (sLine[(mid >> 2) * 12 + (mid & 3)] >= c_min) lo = mid + 1; else hi = mid;
+                        }
+                        n_last = lo;
+                    }
+                }
+                for (int n = n_first; n < n_last; ++n) {
                     int gq = n >> 2, r4 = n & 3;
                     double lc = sLine[gq * 12 + r4], w2 = sLine[gq * 12 + 4 + r4];
                     double rr = sLine[gq * 12 + 8 + r4];

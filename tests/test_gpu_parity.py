@@ -708,3 +708,37 @@ def test_randomised_models_vs_oracle(block):
         assert np.array_equal(np.isneginf(got), np.isneginf(want)), tag
         assert np.isneginf(got[7]), tag
         assert rel_err(got, want).max() < LNPOST_RTOL, (tag, got, want)
+
+
+def test_gaussian_line_profile_cutoff_is_exact():
+    """bc_line_type = gaussian (BC:318-319): the kernel visits only the lines within 27.4 widths of a task
+    (the others are exactly 0.0 in the reference as well, exp underflow).  Narrow to broad widths, on a grid
+    spanning the whole line forest, against the oracle's full 397 x P sum."""
+    from oracle.spamm_numpy import OracleModel
+    from spamm_b200.plan import ModelPlan
+    from spamm_b200.Spectrum import Spectrum
+    wl = grid(2048)
+    comps = ["PL", "BC"]
+    lo = np.array([0., -3., 0., 500., 0., -10., 100., 2.])
+    hi = np.array([1e-13, 3., 1e-13, 1e5, 2., 10., 1e4, 9.])
+    rng = np.random.RandomState(5)
+    params = lo + (hi - lo) * rng.rand(12, 8)
+    params[:, 6] = [100.001, 150., 300., 700., 1500., 3000., 6000., 9999., 120., 450., 2000., 5000.]   # lwidth
+    params[:, 5] = np.linspace(-9.9, 9.9, 12)                                                            # loffset
+    d = 1e-14 * (wl / 5500.) ** -1.5
+    e = 0.05 * d
+    for bc in (True, False):
+        o = OracleModel(wl, d, e, comps=comps, bc=bc, bpc=True, line_type="gaussian")
+        o.set_bounds(lo, hi)
+        with np.errstate(all="ignore"):
+            want = o.ln_posterior_batch(params)
+            want_f = np.array([o.model_flux(p) for p in params])
+        sp = Spectrum(wl, d, e)
+        cs = _components(comps, bc=bc, bpc=True, line_type="gaussian")
+        for cc in cs:
+            cc.initialize(sp)
+        plan = ModelPlan(cs, sp, with_priors=False, bounds=(lo, hi), max_walkers=16)
+        got = plan.lnposterior_host(params)
+        assert rel_err(got, want).max() < LNPOST_RTOL, (bc, got, want)
+        got_f = plan.model_flux_host(params)
+        assert np.max(np.abs(got_f - want_f) / np.max(np.abs(want_f), axis=1, keepdims=True)) < FLUX_RTOL
