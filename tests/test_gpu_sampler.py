@@ -7,6 +7,8 @@ import pytest
 
 from helpers import GOLDEN
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 
@@ -168,3 +170,18 @@ def test_native_loop_equals_python_loop():
     for a, b in zip(*chains):
         assert np.array_equal(a, b)
     assert 0.05 < chains[0][2].mean() / 320 < 0.9
+
+
+@pytest.mark.gpu
+def test_examples_run_configs_script(tmp_path):
+    """examples/run_configs.py (the reference's examples/run_*.py for the BASELINE configs) stays runnable:
+    config 1 for 400 iterations recovers the power-law slope; config 5 runs a short chain."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("run_configs", os.path.join(ROOT, "examples", "run_configs.py"))
+    rc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rc)
+    s, stats, tv = rc.run(1, 400)
+    assert abs(stats[1, 0] - tv[1]) < 5 * max(stats[1, 1], stats[1, 2]) + 0.05          # slope1
+    assert stats[0, 0] <= tv[0] * 1.1                                                   # norm_PL (prior capped at fnw)
+    s, stats, tv = rc.run(5, 20, n_walkers=64)
+    assert stats.shape == (20, 3) and np.all(np.isfinite(stats))
