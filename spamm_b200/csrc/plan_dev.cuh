@@ -90,6 +90,11 @@ struct PlanDev {
     const double *bc_tb0, *bc_tb1, *bc_ta;
     int edge_guess;                       // insertion point of balmer_edge in wl
     int bc_nstage;
+    // adjacent staged pixels 2j, 2j+1: the second sample's two exponentials follow from the first through
+    // expm1 of the (small) argument differences; bc_pair_ok: tau_max |t3[2j+1] - t3[2j]| <= 0.004 everywhere,
+    // bc_dhnu_max: max |h nu[2j+1] - h nu[2j]| (the kernel needs bc_dhnu_max / kT <= 0.01 for the walker)
+    int bc_pair_ok;
+    double bc_dhnu_max;
     double bc_dlnew;
     double c_kms, c_cgs, c_aa, c_cgs2, kb, edge;
     // Extinction (ReddeningLaw.py): k(lambda) of the selected curve, E(B-V) parameter offset; null = absent

@@ -537,6 +537,19 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
             ok = ok && 0.4 * emax * kmax * 2.302585092994046 < 690.0;
         }
         pd.exp_safe = ok ? 1 : 0;
+        pd.bc_pair_ok = 0;
+        pd.bc_dhnu_max = 0.0;
+        if (ok && o_bal >= 0 && pd.bc_on && pd.bc_nstage >= 2) {
+            const double taumax = std::max(std::fabs(d->prior_lo[o_bal + 2]), std::fabs(d->prior_hi[o_bal + 2]));
+            double dt3 = 0.0, dh = 0.0;
+            for (int k = 0; k + 1 < pd.bc_nstage; k += 2) {
+                const double a0 = std::pow(d->wl[k] / d->balmer_edge, 3.0), a1 = std::pow(d->wl[k + 1] / d->balmer_edge, 3.0);
+                dt3 = std::max(dt3, std::fabs(a1 - a0));
+                dh = std::max(dh, std::fabs(d->h_cgs * (d->c_aa / d->wl[k + 1]) - d->h_cgs * (d->c_aa / d->wl[k])));
+            }
+            pd.bc_pair_ok = taumax * dt3 <= 0.004 ? 1 : 0;
+            pd.bc_dhnu_max = dh;
+        }
         double dmax = 0.0;
         for (int i = 0; i + 1 < P; ++i) dmax = std::max(dmax, std::fabs(std::log(d->wl[i + 1] / d->wl[i])));
         pd.nc_pair_ok = (P % 2 == 0 && smax * dmax <= 0.016) ? 1 : 0;
