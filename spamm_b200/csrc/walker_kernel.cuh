@@ -521,43 +521,43 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             sG[n] = rg;      // ratio (n <= 50) or r_n / r_50 (n > 50)
         }
     }
-    // Balmer-continuum samples f0 for the staged pixels; loads batched four deep so one L2 round
-    // trip is exposed per batch instead of per pixel
+    // Balmer-continuum samples f0 for the staged pixels; each trip issues the next trip's loads before
+    // its own arithmetic (no trip is issued for pixels beyond the stage, unlike a batched loop)
     if (do_bc) {
         const int nst = min(pl.bc_nstage, P);
         const double inv_kT = 1.0 / kT;
         if (FULL && pl.bc_pair_ok && pl.bc_dhnu_max * inv_kT <= 0.01) {
-            // adjacent pixel pairs, two pairs in flight per thread
-            for (int k0 = 2 * tid; k0 < nst; k0 += 4 * kThreads) {
-                double2 h[2], kk[2], t3[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int k = min(k0 + 2 * j * kThreads, (nst - 1) & ~1);
-                    h[j] = *reinterpret_cast<const double2*>(pl.bc_hnu + k);
-                    kk[j] = *reinterpret_cast<const double2*>(pl.bc_K + k);
-                    t3[j] = *reinterpret_cast<const double2*>(pl.bc_t3 + k);
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int k = k0 + 2 * j * kThreads;
-                    double f0, f1;
-                    bc_f0_pair(h[j], kk[j], t3[j], inv_kT, b_tau, f0, f1);
-                    if (k < nst) sF0[k] = f0;
-                    if (k + 1 < nst) sF0[k + 1] = f1;
-                }
+            // adjacent pixel pairs, one pair per trip, the next pair's loads issued before this pair's arithmetic
+            int k = 2 * tid;
+            double2 h, kk, t3;
+            if (k < nst) {
+                h = *reinterpret_cast<const double2*>(pl.bc_hnu + k);
+                kk = *reinterpret_cast<const double2*>(pl.bc_K + k);
+                t3 = *reinterpret_cast<const double2*>(pl.bc_t3 + k);
             }
-        } else
-        for (int k0 = tid; k0 < nst; k0 += 4 * kThreads) {
-            double h[4], kk[4], t3[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = min(k0 + j * kThreads, nst - 1);
-                h[j] = pl.bc_hnu[k]; kk[j] = pl.bc_K[k]; t3[j] = pl.bc_t3[k];
+#pragma unroll 1
+            for (; k < nst; k += 2 * kThreads) {
+                const int kn = min(k + 2 * kThreads, (nst - 1) & ~1);
+                const double2 hn = *reinterpret_cast<const double2*>(pl.bc_hnu + kn);
+                const double2 kkn = *reinterpret_cast<const double2*>(pl.bc_K + kn);
+                const double2 t3n = *reinterpret_cast<const double2*>(pl.bc_t3 + kn);
+                double f0, f1;
+                bc_f0_pair(h, kk, t3, inv_kT, b_tau, f0, f1);
+                sF0[k] = f0;
+                if (k + 1 < nst) sF0[k + 1] = f1;
+                h = hn; kk = kkn; t3 = t3n;
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = k0 + j * kThreads;
-                if (k < nst) sF0[k] = bc_f0<FULL>(h[j], kk[j], t3[j], kT, inv_kT, b_tau);
+        } else {
+            // one pixel per trip, the next pixel's loads issued before this pixel's arithmetic
+            int k = tid;
+            double h = 0.0, kk = 0.0, t3 = 0.0;
+            if (k < nst) { h = pl.bc_hnu[k]; kk = pl.bc_K[k]; t3 = pl.bc_t3[k]; }
+#pragma unroll 1
+            for (; k < nst; k += kThreads) {
+                const int kn = min(k + kThreads, nst - 1);
+                const double hn = pl.bc_hnu[kn], kkn = pl.bc_K[kn], t3n = pl.bc_t3[kn];
+                sF0[k] = bc_f0<FULL>(h, kk, t3, kT, inv_kT, b_tau);
+                h = hn; kk = kkn; t3 = t3n;
             }
         }
     }
