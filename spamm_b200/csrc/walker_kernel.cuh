@@ -430,6 +430,9 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     const int n_lines = pl.n_lines, n_pad = pl.n_lines_pad;
     const double kT = pl.kb * b_Te;                      // k.value*T, BC:296
+    // quotients used by the line table (P1) and the cluster constants (P3): divided once per thread
+    const double bal_shift = b_loff / pl.c_kms;          // BC:379
+    const double bal_width = b_lwid / pl.c_kms;
 
     // ---- P1: independent per-walker scalars, spread over the warps ------------------------
     if (tid == 0 && has_nc) {
@@ -502,8 +505,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         }
     }
     if (do_bpc) {
-        const double shift = b_loff / pl.c_kms;          // BC:379
-        const double width = b_lwid / pl.c_kms;
+        const double shift = bal_shift, width = bal_width;
+        const double inv_kT_l = 1.0 / kT;
         // BC:376; only the SH95 look-ups (n <= 50, the first threads) use it
         const double n_e = pl.line_min + tid <= 50 ? pow(10.0, b_logNe) : 0.0;
         for (int n = tid; n < n_pad; n += kThreads) {
@@ -514,7 +517,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 wv = width * lc;                         // BC:316
                 int nn = pl.line_min + n;
                 if (nn <= 50) rg = sh95_bilinear(pl, 50 - nn, n_e, b_Te);   // coef_use[-i+2], BC:294
-                else rg = exp(pl.line_cum[n] / kT);                          // BC:296, telescoped
+                else rg = FULL ? exp_fast<false>(pl.line_cum[n] * inv_kT_l)    // |S_n / kT| <= 0.2 (PlanDev::mom_poly)
+                               : exp(pl.line_cum[n] / kT);                    // BC:296, telescoped
             }
             sLine[(n >> 2) * 12 + (n & 3)] = lc;
             sW[n] = wv;
@@ -642,12 +646,12 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
                 double acc = g[kMomPoly - 1];
 #pragma unroll
                 for (int q = kMomPoly - 2; q >= 0; --q) acc = fma(acc, z, g[q]);
-                const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
+                const double shift = bal_shift, width = bal_width;
                 mk[0] = fma(r50 * (width * (1.0 - shift)), acc, mk[0]);
             }
             if (!(lane & 1)) c.cw[kcl].mom[lane >> 1] = mk[0];
             if (lane == 0) {
-                const double shift = b_loff / pl.c_kms, width = b_lwid / pl.c_kms;
+                const double shift = bal_shift, width = bal_width;
                 const double kappa = width * width;
                 const double cb = cd.cb0 - shift * cd.cb0, R = cd.R0 - shift * cd.R0;
                 ClusterW& cw = c.cw[kcl];
