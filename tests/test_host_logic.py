@@ -188,3 +188,43 @@ def test_sampler_argument_checks():
         EnsembleSampler(nwalkers=31, dim=2, plan=object())
     with pytest.raises(AssertionError):
         EnsembleSampler(nwalkers=30, dim=20, plan=object())
+
+
+def test_balmer_continuum_pair_recurrence_accuracy():
+    """The specialised kernel stages the Balmer continuum on adjacent pixel pairs: the second sample's
+    expm1(h nu / kT) and exp(-tau t3) follow from the first through expm1 of the argument differences, a
+    degree-6 / degree-5 Taylor series (walker_kernel.cuh, bc_f0_pair).  The same algebra in numpy against
+    80-bit evaluation of the same arguments, over the part of the prior box where the kernel takes that
+    path (max |d h nu| / kT <= 0.01) on the BASELINE config-5 grid: the recurrence is as accurate as the
+    direct double-precision evaluation (both carry the x * 2^-53 conditioning of exp at x = h nu / kT)."""
+    from spamm_b200 import constants as C
+    L = np.longdouble
+    wl = grid(8192)
+    wl = wl[wl < 3660.0]
+    h, kb, c_aa = C.H_CGS, C.KB_CGS, C.C_AA
+    hnu = h * (c_aa / wl)
+    t3 = (wl / 3646.0) ** 3
+    h0, h1, t0, t1 = hnu[0:-1:2], hnu[1::2], t3[0:-1:2], t3[1::2]
+    dh_max = np.max(np.abs(h1 - h0))
+    for Te in (dh_max / (0.01 * kb) * 1.0001, 2.5e4, 5.025e4, 8.0e4, 9.99e4):
+        inv_kT = 1.0 / (kb * Te)
+        assert dh_max * inv_kT <= 0.01
+        truth = np.expm1(L(h1) * L(inv_kT))
+        direct = np.expm1(h1 * inv_kT)
+        bm0 = np.expm1(h0 * inv_kT)
+        dx = (h1 - h0) * inv_kT
+        p = ((((dx / 720.0 + 1.0 / 120.0) * dx + 1.0 / 24.0) * dx + 1.0 / 6.0) * dx + 0.5) * dx + 1.0
+        p = p * dx
+        bm1 = p * (bm0 + 1.0) + bm0
+        err_direct = np.max(np.abs(L(direct) - truth) / truth)
+        err_rec = np.max(np.abs(L(bm1) - truth) / truth)
+        assert err_rec <= 2.0 * err_direct + 5e-16, (Te, float(err_rec), float(err_direct))
+        for tau in (1e-3, 0.5, 1.0, 2.0):
+            truth = np.exp(-(L(tau) * L(t1)))
+            e0 = np.exp(-tau * t0)
+            dt = tau * (t0 - t1)
+            assert np.max(np.abs(dt)) <= 0.004
+            q = (((dt / 120.0 + 1.0 / 24.0) * dt + 1.0 / 6.0) * dt + 0.5) * dt + 1.0
+            q = q * dt
+            e1 = e0 * q + e0
+            assert np.max(np.abs(L(e1) - truth) / truth) <= 6e-16, (Te, tau)
