@@ -569,7 +569,10 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     SPAMM_SMEM_ATTR(0, true, false, 1); SPAMM_SMEM_ATTR(0, true, true, 1);
     SPAMM_SMEM_ATTR(0, true, false, 3); SPAMM_SMEM_ATTR(0, true, true, 3);
     SPAMM_SMEM_ATTR(0, true, false, 5); SPAMM_SMEM_ATTR(0, true, true, 5);
+    SPAMM_SMEM_ATTR(0, true, false, 7); SPAMM_SMEM_ATTR(0, true, true, 7);
     SPAMM_SMEM_ATTR(0, true, false, 9); SPAMM_SMEM_ATTR(0, true, true, 9);
+    SPAMM_SMEM_ATTR(0, true, false, 11); SPAMM_SMEM_ATTR(0, true, true, 11);
+    SPAMM_SMEM_ATTR(0, true, false, 13); SPAMM_SMEM_ATTR(0, true, true, 13);
     SPAMM_SMEM_ATTR(0, true, false, 15); SPAMM_SMEM_ATTR(0, true, true, 15);
     SPAMM_SMEM_ATTR(0, true, false, 31); SPAMM_SMEM_ATTR(0, true, true, 31);
 #undef SPAMM_SMEM_ATTR
@@ -732,8 +735,8 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
         return c > 1 ? launch_one<0, true, true, S>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po) \
                      : launch_one<0, true, false, S>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
         switch (spec_of(pl, pd, mask, dr)) {
-            SPAMM_LAUNCH_SPEC(1) SPAMM_LAUNCH_SPEC(3) SPAMM_LAUNCH_SPEC(5) SPAMM_LAUNCH_SPEC(9)
-            SPAMM_LAUNCH_SPEC(15) SPAMM_LAUNCH_SPEC(31)
+            SPAMM_LAUNCH_SPEC(1) SPAMM_LAUNCH_SPEC(3) SPAMM_LAUNCH_SPEC(5) SPAMM_LAUNCH_SPEC(7) SPAMM_LAUNCH_SPEC(9)
+            SPAMM_LAUNCH_SPEC(11) SPAMM_LAUNCH_SPEC(13) SPAMM_LAUNCH_SPEC(15) SPAMM_LAUNCH_SPEC(31)
             default: break;
         }
 #undef SPAMM_LAUNCH_SPEC

@@ -331,7 +331,8 @@ constexpr int kFullFe = 3, kFullHost = 7, kFullClusters = 4, kFullSuper = 3;
 // always bit 0; kSpecFe: Fe x3, kSpecHost: host x7, kSpecBalmer: BalmerCombined with both parts on,
 // Lorentzian + series, kSpecExt: a trailing Extinction); the supported sets are listed in kSpecs.
 constexpr int kSpecNc = 1, kSpecFe = 2, kSpecHost = 4, kSpecBalmer = 8, kSpecExt = 16;
-constexpr int kSpecs[] = {1, 3, 5, 9, 15, 31};    // NC | NC+Fe | NC+host | NC+Balmer | full | full+Extinction
+// NC | NC+Fe | NC+host | NC+Fe+host | NC+Balmer | NC+Fe+Balmer | NC+host+Balmer | full | full+Extinction
+constexpr int kSpecs[] = {1, 3, 5, 7, 9, 11, 13, 15, 31};
 template <int MODE, bool CANON, bool SPLIT, int SPEC>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,

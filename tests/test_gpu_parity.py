@@ -742,3 +742,38 @@ def test_gaussian_line_profile_cutoff_is_exact():
         assert rel_err(got, want).max() < LNPOST_RTOL, (bc, got, want)
         got_f = plan.model_flux_host(params)
         assert np.max(np.abs(got_f - want_f) / np.max(np.abs(want_f), axis=1, keepdims=True)) < FLUX_RTOL
+
+
+@pytest.mark.parametrize("comps", [["PL", "FE", "HOST"], ["PL", "FE", "BC"], ["PL", "HOST", "BC"]])
+def test_specialised_three_component_models(comps, monkeypatch):
+    """The three-component subsets in run_spamm's order (e.g. PL + FE + BC, the usual UV fit without a host)
+    have their own specialised instantiations: against the oracle, the generic instantiation and every
+    walker split."""
+    from oracle.spamm_numpy import OracleModel
+    wl = grid(2048)
+    o0 = OracleModel(wl, wl, wl, comps=comps)
+    fl = [o0.component_flux(c, TRUTH[c]) for c in comps]
+    rng = np.random.RandomState(17)
+    d = np.sum(fl, axis=0) * (1 + 0.02 * rng.standard_normal(len(wl)))
+    e = np.sqrt(np.sum([(0.05 * f) ** 2 for f in fl], axis=0))
+    o = OracleModel(wl, d, e, comps=comps)
+    np.random.seed(23)
+    params = np.array([o.initial_values() for _ in range(40)])
+    params[3, 0] = -1.0                                          # one walker outside the prior box
+    want = o.ln_posterior_batch(params)
+    c = Case.__new__(Case)
+    c.wl, c.flux, c.err, c.comps, c.bc, c.bpc = wl, d, e, comps, True, True
+    m = _model(c)
+    assert m.plan.specialised
+    got = m.lnposterior_batch(params)
+    assert np.isneginf(got[3]) and np.isneginf(want[3])
+    assert rel_err(got, want).max() < LNPOST_RTOL
+    monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+    g = _model(c)
+    assert not g.plan.specialised
+    ref = g.lnposterior_batch(params)
+    monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
+    assert rel_err(got, ref).max() < 1e-13
+    for split in (2, 4, 8):
+        m.plan.set_walker_split(split)
+        assert np.array_equal(m.lnposterior_batch(params), got)

@@ -13,7 +13,10 @@ CONFIGS = (("cfg2 NC+Fe, 1024 walkers x 4096 px", ("PL", "FE"), 4096, 1024),
            ("cfg3 NC+host, 2048 walkers x 8192 px", ("PL", "HOST"), 8192, 2048),
            ("cfg4 NC+Balmer, 4096 walkers x 8192 px", ("PL", "BC"), 8192, 4096),
            ("cfg5 full, 8192 walkers x 8192 px", ("PL", "FE", "HOST", "BC"), 8192, 8192),
-           ("full + MW extinction, 8192 x 8192", ("PL", "FE", "HOST", "BC", "MW_EXT"), 8192, 8192))
+           ("full + MW extinction, 8192 x 8192", ("PL", "FE", "HOST", "BC", "MW_EXT"), 8192, 8192),
+           ("NC+Fe+host, 8192 x 8192", ("PL", "FE", "HOST"), 8192, 8192),
+           ("NC+Fe+Balmer, 8192 x 8192", ("PL", "FE", "BC"), 8192, 8192),
+           ("NC+host+Balmer, 8192 x 8192", ("PL", "HOST", "BC"), 8192, 8192))
 for name, comps, P, W in CONFIGS:
     wl = config_grid(P)
     base = tuple(c for c in comps if not c.endswith("_EXT"))
