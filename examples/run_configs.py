@@ -56,7 +56,10 @@ def run(config, n_iterations, n_walkers=None, seed=1):
     flux = flux + err * rng.standard_normal(len(wl))          # one noise realisation of the 5 % errors
     outdir = tempfile.mkdtemp(prefix="spamm_b200_cfg%d_" % config)
     t0 = time.time()
-    out = spamm(list(components), (wl, flux, err), n_walkers=walkers, n_iterations=n_iterations,
+    # "BC" alone switches on the Balmer continuum only (run_spamm.py:118-121); the BASELINE configurations
+    # fit the continuum together with the high-order lines, like create_bc generates them
+    complist = [x for c in components for x in (("BC", "BPC") if c == "BC" else (c,))]
+    out = spamm(complist, (wl, flux, err), n_walkers=walkers, n_iterations=n_iterations,
                 outdir=outdir, picklefile="cfg%d" % config, seed=seed)
     dt = time.time() - t0
     model = out["model"]
