@@ -574,6 +574,10 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     SPAMM_SMEM_ATTR(0, true, false, 11); SPAMM_SMEM_ATTR(0, true, true, 11);
     SPAMM_SMEM_ATTR(0, true, false, 13); SPAMM_SMEM_ATTR(0, true, true, 13);
     SPAMM_SMEM_ATTR(0, true, false, 15); SPAMM_SMEM_ATTR(0, true, true, 15);
+    SPAMM_SMEM_ATTR(0, true, false, 41); SPAMM_SMEM_ATTR(0, true, true, 41);
+    SPAMM_SMEM_ATTR(0, true, false, 73); SPAMM_SMEM_ATTR(0, true, true, 73);
+    SPAMM_SMEM_ATTR(0, true, false, 47); SPAMM_SMEM_ATTR(0, true, true, 47);
+    SPAMM_SMEM_ATTR(0, true, false, 79); SPAMM_SMEM_ATTR(0, true, true, 79);
     SPAMM_SMEM_ATTR(0, true, false, 31); SPAMM_SMEM_ATTR(0, true, true, 31);
 #undef SPAMM_SMEM_ATTR
     CUDA_TRY(cudaDeviceSynchronize());
@@ -708,9 +712,11 @@ static int spec_of(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, const 
         else if (kind == SPAMM_COMP_FE) { if (pd.fe.n_templ != kFullFe) return 0; spec |= kSpecFe; }
         else if (kind == SPAMM_COMP_HOST) { if (pd.host.n_templ != kFullHost) return 0; spec |= kSpecHost; }
         else if (kind == SPAMM_COMP_BALMER) {
-            if (!(pd.bc_on && pd.bpc_on && pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on &&
-                  pd.n_clusters == kFullClusters && pd.n_super == kFullSuper)) return 0;
+            if (pd.bpc_on && !(pd.line_type == SPAMM_LINE_LORENTZIAN && pd.series_on &&
+                               pd.n_clusters == kFullClusters && pd.n_super == kFullSuper)) return 0;
             spec |= kSpecBalmer;
+            if (!pd.bpc_on) spec |= kSpecNoBpc;
+            if (!pd.bc_on) spec |= kSpecNoBc;
         } else if (kind == SPAMM_COMP_EXTINCTION) spec |= kSpecExt;
     }
     for (int k : kSpecs) if (k == spec) return spec;
@@ -737,6 +743,7 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
         switch (spec_of(pl, pd, mask, dr)) {
             SPAMM_LAUNCH_SPEC(1) SPAMM_LAUNCH_SPEC(3) SPAMM_LAUNCH_SPEC(5) SPAMM_LAUNCH_SPEC(7) SPAMM_LAUNCH_SPEC(9)
             SPAMM_LAUNCH_SPEC(11) SPAMM_LAUNCH_SPEC(13) SPAMM_LAUNCH_SPEC(15) SPAMM_LAUNCH_SPEC(31)
+            SPAMM_LAUNCH_SPEC(41) SPAMM_LAUNCH_SPEC(73) SPAMM_LAUNCH_SPEC(47) SPAMM_LAUNCH_SPEC(79)
             default: break;
         }
 #undef SPAMM_LAUNCH_SPEC

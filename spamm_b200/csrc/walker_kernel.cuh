@@ -331,8 +331,12 @@ constexpr int kFullFe = 3, kFullHost = 7, kFullClusters = 4, kFullSuper = 3;
 // always bit 0; kSpecFe: Fe x3, kSpecHost: host x7, kSpecBalmer: BalmerCombined with both parts on,
 // Lorentzian + series, kSpecExt: a trailing Extinction); the supported sets are listed in kSpecs.
 constexpr int kSpecNc = 1, kSpecFe = 2, kSpecHost = 4, kSpecBalmer = 8, kSpecExt = 16;
-// NC | NC+Fe | NC+host | NC+Fe+host | NC+Balmer | NC+Fe+Balmer | NC+host+Balmer | full | full+Extinction
-constexpr int kSpecs[] = {1, 3, 5, 7, 9, 11, 13, 15, 31};
+// modifiers of kSpecBalmer: BalmerCombined with one part switched off -- run_spamm's "BC" without "BPC" is the
+// continuum alone (run_spamm.py:118-121; the reference's own examples/test_spamm.py fits that model)
+constexpr int kSpecNoBpc = 32, kSpecNoBc = 64;
+// NC | NC+Fe | NC+host | NC+Fe+host | NC+Balmer | NC+Fe+Balmer | NC+host+Balmer | full | full+Extinction |
+// NC+Balmer and full with the continuum only / the lines only
+constexpr int kSpecs[] = {1, 3, 5, 7, 9, 11, 13, 15, 31, 9 | kSpecNoBpc, 9 | kSpecNoBc, 15 | kSpecNoBpc, 15 | kSpecNoBc};
 template <int MODE, bool CANON, bool SPLIT, int SPEC>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
@@ -414,8 +418,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const bool have_balmer = FULL ? (SPEC & kSpecBalmer) != 0 : off_bal >= 0;
     const int n_fe = FULL ? NFE : (has_fe ? pl.fe.n_templ : 0);
     const int n_host = FULL ? NHOST : (has_host ? pl.host.n_templ : 0);
-    const bool do_bc = FULL ? have_balmer : have_balmer && pl.bc_on;
-    const bool do_bpc = FULL ? have_balmer : have_balmer && pl.bpc_on;
+    const bool do_bc = FULL ? have_balmer && (SPEC & kSpecNoBc) == 0 : have_balmer && pl.bc_on;
+    const bool do_bpc = FULL ? have_balmer && (SPEC & kSpecNoBpc) == 0 : have_balmer && pl.bpc_on;
     const bool lorentz = FULL ? true : pl.line_type == SPAMM_LINE_LORENTZIAN;
     const bool series_on = FULL ? true : pl.series_on != 0;
     constexpr bool PAIR = FULL && kPix == 2;      // adjacent-pixel lanes with 16-byte loads

@@ -777,3 +777,40 @@ def test_specialised_three_component_models(comps, monkeypatch):
     for split in (2, 4, 8):
         m.plan.set_walker_split(split)
         assert np.array_equal(m.lnposterior_batch(params), got)
+
+
+@pytest.mark.parametrize("comps", [["PL", "BC"], ["PL", "FE", "HOST", "BC"]])
+@pytest.mark.parametrize("bc,bpc", [(True, False), (False, True)])
+def test_specialised_balmer_with_one_part_off(comps, bc, bpc, monkeypatch):
+    """run_spamm's "BC" without "BPC" is the Balmer continuum alone (run_spamm.py:118-121; the reference's
+    examples/test_spamm.py fits exactly that), "BPC" alone the line forest alone: both have specialised
+    instantiations for NC + Balmer and for the full model."""
+    from oracle.spamm_numpy import OracleModel
+    wl = grid(2048)
+    o0 = OracleModel(wl, wl, wl, comps=comps)
+    fl = [o0.component_flux(c, TRUTH[c]) for c in comps]
+    rng = np.random.RandomState(29)
+    d = np.sum(fl, axis=0) * (1 + 0.02 * rng.standard_normal(len(wl)))
+    e = np.sqrt(np.sum([(0.05 * f) ** 2 for f in fl], axis=0))
+    o = OracleModel(wl, d, e, comps=comps, bc=bc, bpc=bpc)
+    np.random.seed(31)
+    params = np.array([o.initial_values() for _ in range(40)])
+    params[5, 1] = 3.5                                           # slope outside the prior box
+    want = o.ln_posterior_batch(params)
+    c = Case.__new__(Case)
+    c.wl, c.flux, c.err, c.comps, c.bc, c.bpc = wl, d, e, comps, bc, bpc
+    m = _model(c)
+    assert m.plan.specialised
+    got = m.lnposterior_batch(params)
+    assert np.isneginf(got[5]) and np.isneginf(want[5])
+    assert rel_err(got, want).max() < LNPOST_RTOL
+    monkeypatch.setenv("SPAMM_NO_FULL_KERNEL", "1")
+    g = _model(c)
+    assert not g.plan.specialised
+    ref = g.lnposterior_batch(params)
+    monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
+    assert rel_err(got, ref).max() < 1e-13
+    for split in (2, 4, 8):
+        m.plan.set_walker_split(split)
+        assert np.array_equal(m.lnposterior_batch(params), got)
+    assert m.plan.status() == 0
