@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SPAMM_ABI_VERSION 2
+#define SPAMM_ABI_VERSION 3
 #define SPAMM_MAX_COMPONENTS 8
 #define SPAMM_MAX_TEMPLATES 16
 #define SPAMM_SH95_NE 7
@@ -35,7 +35,8 @@ extern "C" {
 #define SPAMM_EINVAL (-1)     /* bad argument / unsupported configuration */
 #define SPAMM_ECUDA (-2)      /* CUDA runtime error */
 #define SPAMM_ENOMEM (-3)
-#define SPAMM_ERANGE (-4)     /* a walker needed a value outside the plan's tables */
+#define SPAMM_ERANGE (-4)     /* a walker needed a value outside the plan's tables, or a peer rank's
+                                 results never arrived: the numbers of that call are not the model's */
 
 /* Model.components entries, spamm/run_spamm.py:100-122 */
 enum SpammComponentKind {
@@ -153,7 +154,8 @@ int spamm_lnpost_batch_p2p(SpammPlan* plan, const double* params_dev, int32_t n_
                            void* stream);
 
 /* Same call with HOST buffers: pinned staging, H2D, kernel, D2H, synchronise.
- * This is what an emcee `pool.map` adapter binds (Model.py:283-289). */
+ * This is what an emcee `pool.map` adapter binds (Model.py:283-289).
+ * Returns SPAMM_ERANGE (and clears the condition) if any walker set the device status word. */
 int spamm_lnpost_batch_host(SpammPlan* plan, const double* params_host, int32_t n_walkers,
                             double* lnp_host);
 
@@ -183,6 +185,12 @@ int spamm_plan_specialised(const SpammPlan* plan);
 /* Device status word (0 = ok); synchronises `stream`.  Non-zero means some walker
  * needed a table entry outside the plan (SPAMM_ERANGE conditions). */
 int spamm_plan_status(SpammPlan* plan, void* stream);
+/* Same check as an error code: synchronises `stream`, returns SPAMM_ERANGE with the conditions spelled
+ * out in spamm_last_error() and clears the word, or SPAMM_OK.  The synchronous entry points
+ * (spamm_lnpost_batch_host, spamm_lnpost_batch_sharded_host) make this check themselves; the
+ * asynchronous ones queue a copy of the word behind their kernels and the NEXT call on the plan
+ * returns the error -- call spamm_plan_check where you synchronise (end of a chain) to be sure. */
+int spamm_plan_check(SpammPlan* plan, void* stream);
 /* number of kernels the library has launched on this plan since creation */
 int64_t spamm_plan_launch_count(const SpammPlan* plan);
 
@@ -190,7 +198,10 @@ int64_t spamm_plan_launch_count(const SpammPlan* plan);
  * resident CTA slots the fused kernel runs one walker per thread-block CLUSTER and deals the
  * walker's pixel tasks over the cluster's CTAs; the chi^2 partials are gathered through
  * distributed shared memory in the same fixed order, so results do not depend on the split.
- * mode 0: off; 1: automatic (default; 2/4/8 CTAs by ensemble size); 2, 4, 8: forced. */
+ * Ensembles of one to a few waves of CTAs (a half-ensemble shard on one of 8 GPUs) can instead run each
+ * walker as two independent CTAs -- the pixels redward of the Balmer edge with the line table, the pixels
+ * blueward with the Balmer continuum stage -- with dynamically dealt tasks; same bits again.
+ * mode 0: off; 1: automatic (default); 2, 4, 8: forced cluster size; 3: forced two-part split. */
 int spamm_plan_set_walker_split(SpammPlan* plan, int32_t mode);
 
 /* emcee 2.2.1 stretch move (EnsembleSampler._propose_stretch; call site
@@ -222,6 +233,53 @@ int spamm_stretch_run(SpammPlan* plan, double* walkers_dev, double* lnp_dev, int
                       uint64_t seed, uint64_t iter0, int32_t n_iter, double* q_dev, double* z_dev,
                       double* lnp_q_dev, int64_t* naccepted_dev, double* chain_dev, double* lnp_chain_dev,
                       int64_t chain_len, void* stream);
+
+/* ---- multi-GPU: walker shards, results exchanged by the compute kernel itself -------------------
+ * Replaces the task farm of emcee's pool (spamm/Model.py:264-289: pickled (Model, params) tasks out,
+ * floats back).  Every rank holds the replicated ensemble and the same counter-based RNG; a sharded call
+ * evaluates walkers [lo, hi) = spamm_shard_bounds(n, n_ranks, rank) on this rank, and the walker kernel
+ * stores each ln-posterior directly into EVERY rank's exchange region (peer-to-peer stores over NVLink)
+ * and, when its last walker retires, raises this rank's flag in every region.  Consumers wait on the
+ * flags on the device; there is no host-side barrier and no collective on the data path.
+ * All ranks must make the same sequence of sharded calls (the epoch counter is implicit). */
+typedef struct SpammExchange SpammExchange;
+#define SPAMM_IPC_HANDLE_BYTES 64
+void spamm_shard_bounds(int64_t n, int32_t n_ranks, int32_t rank, int64_t* lo, int64_t* hi);
+int64_t spamm_exchange_region_bytes(int64_t max_walkers);
+/* Allocate this rank's region on the current device (flag block + two result buffers of max_walkers
+ * doubles).  ipc_handle_out (SPAMM_IPC_HANDLE_BYTES, may be NULL) receives the CUDA IPC handle the other
+ * processes of the box need; n_ranks == 1 is connected immediately. */
+int spamm_exchange_create(int32_t n_ranks, int32_t rank, int64_t max_walkers, SpammExchange** out,
+                          void* ipc_handle_out);
+/* all_handles: [n_ranks][SPAMM_IPC_HANDLE_BYTES] gathered from every rank by any transport
+ * (torch.distributed.all_gather, MPI, a file).  Peer access is enabled as the handles are opened.
+ * The caller must barrier after connecting and before destroying. */
+int spamm_exchange_connect(SpammExchange* ex, const void* all_handles);
+/* Same-process variant (several ranks as threads/streams of one process, or regions mapped by the
+ * caller, e.g. torch symmetric memory): region_ptrs[r] = rank r's region as addressable from here. */
+int spamm_exchange_connect_ptrs(SpammExchange* ex, const uint64_t* region_ptrs);
+uint64_t spamm_exchange_region_ptr(const SpammExchange* ex);
+uint64_t spamm_exchange_epoch(const SpammExchange* ex);
+void spamm_exchange_destroy(SpammExchange* ex);
+
+/* spamm_lnpost_batch over a sharded ensemble: params_dev is the FULL replicated [n_total][D] array
+ * (only this rank's rows are read).  Queues on `stream`: the walker kernel on this rank's slice (results
+ * and flag to every rank), then a wait for every rank's flag, then -- if lnp_dev != NULL -- a copy of the
+ * gathered [n_total] vector to lnp_dev.  *lnp_region_out (may be NULL) is the vector inside this rank's
+ * region; it stays valid until the second-next sharded call. */
+int spamm_lnpost_batch_sharded(SpammPlan* plan, SpammExchange* ex, const double* params_dev, int32_t n_total,
+                               double* lnp_dev, const double** lnp_region_out, void* stream);
+/* Host-buffer form: H2D of this rank's parameter rows only, kernel + exchange, D2H of the whole gathered
+ * vector, synchronise, status check.  params_host is the full [n_total][D] array on every rank. */
+int spamm_lnpost_batch_sharded_host(SpammPlan* plan, SpammExchange* ex, const double* params_host,
+                                    int32_t n_total, double* lnp_host);
+/* spamm_stretch_run with every half-step's proposals sharded over the ranks: propose (replicated), walker
+ * kernel on this rank's slice (P2P stores + flag), accept after the flag wait inside the accept kernel.
+ * Chains are bit-identical to the single-device run with the same seed. */
+int spamm_stretch_run_sharded(SpammPlan* plan, SpammExchange* ex, double* walkers_dev, double* lnp_dev,
+                              int32_t n_walkers, double a, uint64_t seed, uint64_t iter0, int32_t n_iter,
+                              double* q_dev, double* z_dev, int64_t* naccepted_dev, double* chain_dev,
+                              double* lnp_chain_dev, int64_t chain_len, void* stream);
 
 /* FP64 FMA throughput probe (roofline denominator: MEASURED_PEAKS.json has no
  * FP64 entry).  Runs `iters` dependent-chain DFMA iterations on every SM and

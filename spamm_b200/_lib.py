@@ -9,7 +9,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPAMM_B200_LIB", os.path.join(PKG, "libspamm_b200.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_COMPONENTS = 8
 MAX_TEMPLATES = 16
 SH95_NE, SH95_T, SH95_LINES = 7, 10, 48
@@ -85,8 +85,12 @@ EXPORTS = [
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
     "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split", "spamm_plan_specialised",
     "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record", "spamm_stretch_run",
-    "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version",
+    "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version", "spamm_plan_check",
+    "spamm_shard_bounds", "spamm_exchange_region_bytes", "spamm_exchange_create", "spamm_exchange_connect",
+    "spamm_exchange_connect_ptrs", "spamm_exchange_region_ptr", "spamm_exchange_epoch", "spamm_exchange_destroy",
+    "spamm_lnpost_batch_sharded", "spamm_lnpost_batch_sharded_host", "spamm_stretch_run_sharded",
 ]
+IPC_HANDLE_BYTES = 64
 
 _lib = None
 
@@ -150,6 +154,30 @@ def load():
     lib.spamm_chain_record.restype = ctypes.c_int
     lib.spamm_stretch_run.argtypes = [vp, vp, vp, i32, dbl, u64, u64, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.spamm_stretch_run.restype = ctypes.c_int
+    lib.spamm_plan_check.argtypes = [vp, vp]
+    lib.spamm_plan_check.restype = ctypes.c_int
+    lib.spamm_shard_bounds.argtypes = [i64, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.spamm_shard_bounds.restype = None
+    lib.spamm_exchange_region_bytes.argtypes = [i64]
+    lib.spamm_exchange_region_bytes.restype = i64
+    lib.spamm_exchange_create.argtypes = [i32, i32, i64, ctypes.POINTER(vp), vp]
+    lib.spamm_exchange_create.restype = ctypes.c_int
+    lib.spamm_exchange_connect.argtypes = [vp, vp]
+    lib.spamm_exchange_connect.restype = ctypes.c_int
+    lib.spamm_exchange_connect_ptrs.argtypes = [vp, ctypes.POINTER(u64)]
+    lib.spamm_exchange_connect_ptrs.restype = ctypes.c_int
+    lib.spamm_exchange_region_ptr.argtypes = [vp]
+    lib.spamm_exchange_region_ptr.restype = u64
+    lib.spamm_exchange_epoch.argtypes = [vp]
+    lib.spamm_exchange_epoch.restype = u64
+    lib.spamm_exchange_destroy.argtypes = [vp]
+    lib.spamm_exchange_destroy.restype = None
+    lib.spamm_lnpost_batch_sharded.argtypes = [vp, vp, vp, i32, vp, ctypes.POINTER(vp), vp]
+    lib.spamm_lnpost_batch_sharded.restype = ctypes.c_int
+    lib.spamm_lnpost_batch_sharded_host.argtypes = [vp, vp, vp, i32, vp]
+    lib.spamm_lnpost_batch_sharded_host.restype = ctypes.c_int
+    lib.spamm_stretch_run_sharded.argtypes = [vp, vp, vp, vp, i32, dbl, u64, u64, i32, vp, vp, vp, vp, vp, i64, vp]
+    lib.spamm_stretch_run_sharded.restype = ctypes.c_int
     lib.spamm_fp64_peak_probe.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.spamm_fp64_peak_probe.restype = ctypes.c_int
     lib.spamm_last_error.argtypes = []

@@ -70,6 +70,14 @@ class Component(ABC):
         return PARS["rebin_spec"] is False
 
     # -- device path ---------------------------------------------------------
+    def __getstate__(self):
+        """Pickle without the cached device plans of flux() (ctypes handles; rebuilt on demand) -- the
+        reference's components stay picklable after any call (run_spamm.py:157-160 pickles the Model)."""
+        d = dict(self.__dict__)
+        if "_flux_plans" in d:
+            d["_flux_plans"] = {}
+        return d
+
     @abstractmethod
     def prior_bounds(self, spectrum=None):
         """(lo, hi) lists of the flat-box priors, resolving the string

@@ -25,7 +25,9 @@ enum StatusBits : int {
     kStatSigmaRange = 1,   // sigma_norm outside the bank / < 1
     kStatBcKernel = 2,     // log_conv kernel wider than one pixel (unsupported)
     kStatBcStage = 4,      // BC edge pixel beyond the staged f0 range
+    kStatPeerTimeout = 8,  // multi-GPU exchange: a peer's flag did not arrive within 5 s
 };
+constexpr int kFlagWords = 64;         // flag block at the start of an exchange region (one word per rank)
 
 constexpr int kMaxClusters = 8;        // base clusters + nested supersets
 constexpr int kMom = 16;               // series terms kept (validated: <= 1e-15 at rho <= 0.1)
@@ -90,6 +92,9 @@ struct PlanDev {
     const double *bc_tb0, *bc_tb1, *bc_ta;
     int edge_guess;                       // insertion point of balmer_edge in wl
     int bc_nstage;
+    // walker parts (k_walkers, kSpecParts): chunks [part_chunk, n_chunks) hold every pixel beyond the Balmer
+    // edge of any in-prior walker; a red part stages f0 from part_stage0 (even) on; part_chunk < 0: not available
+    int part_chunk, part_stage0;
     // adjacent staged pixels 2j, 2j+1: the second sample's two exponentials follow from the first through
     // expm1 of the (small) argument differences; bc_pair_ok: tau_max |t3[2j+1] - t3[2j]| <= 0.004 everywhere,
     // bc_dhnu_max: max |h nu[2j+1] - h nu[2j]| (the kernel needs bc_dhnu_max / kT <= 0.01 for the walker)
@@ -103,5 +108,12 @@ struct PlanDev {
     int fe_rows, host_rows;               // rows in the sigma banks
     int exp_safe;                         // the prior box bounds every exp() argument of the fused kernel
     int nc_pair_ok;                       // P even and |slope| |ln(wl[i+1]/wl[i])| <= 0.016 inside the prior box
-    int* status;
+    int* status;                          // sticky device status word (StatusBits)
+    int* status_host;                     // mapped pinned host word: set non-zero together with `status`, so the
+                                          // host notices without queueing a copy behind every kernel
 };
+
+__device__ __forceinline__ void flag_status(int* status, int* status_host, int bit) {
+    atomicOr(status, bit);
+    *reinterpret_cast<volatile int*>(status_host) = 1;
+}

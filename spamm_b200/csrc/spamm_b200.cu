@@ -73,7 +73,11 @@ struct SpammPlan {
     cudaStream_t own_stream = nullptr;
     int max_sigma_seen = 0;
     int last_bank_rows = 0;
-    int split_mode = 1;          // 0: never split a walker over a cluster; 1: auto; 2/4/8: forced size
+    int split_mode = 1;          // 0: never split a walker; 1: auto; 2/4/8: forced cluster size; 3: forced two-part split
+    int* h_status = nullptr;           // pinned copy of the device status word (mapped; see deferred_status)
+    double* d_part_chi = nullptr;      // walker parts: per-chunk chi^2 partials [max_walkers][n_chunks]
+    unsigned* d_part_cnt = nullptr;    //               arrival counters [max_walkers]
+    int parts_max_walkers = getenv("SPAMM_PARTS_MAX") ? atoi(getenv("SPAMM_PARTS_MAX")) : 0;   // auto two-part split up to here (0: default)
     bool use_full_kernel = getenv("SPAMM_NO_FULL_KERNEL") == nullptr;   // tests compare it with the generic one
 };
 
@@ -218,8 +222,10 @@ extern "C" void spamm_plan_destroy(SpammPlan* pl) {
     cudaFree(pl->d_conv); cudaFree(pl->d_fe_f); cudaFree(pl->d_fe_nf);
     cudaFree(pl->d_host_f); cudaFree(pl->d_host_nf); cudaFree(pl->d_row_t); cudaFree(pl->d_row_sig);
     cudaFree(pl->d_params); cudaFree(pl->d_lnp);
+    cudaFree(pl->d_part_chi); cudaFree(pl->d_part_cnt);
     if (pl->h_params) cudaFreeHost(pl->h_params);
     if (pl->h_lnp) cudaFreeHost(pl->h_lnp);
+    if (pl->h_status) cudaFreeHost(pl->h_status);
     if (pl->own_stream) cudaStreamDestroy(pl->own_stream);
     delete pl;
 }
@@ -265,6 +271,9 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     }
     if ((rc = dalloc(pl, 1, &pd.status))) return rc;
     CUDA_TRY(cudaMemset(pd.status, 0, sizeof(int)));
+    CUDA_TRY(cudaHostAlloc(&pl->h_status, sizeof(int), cudaHostAllocMapped));
+    *pl->h_status = 0;
+    CUDA_TRY(cudaHostGetDevicePointer(&pd.status_host, pl->h_status, 0));
     if ((rc = dalloc(pl, 1, &pl->d_flag))) return rc;
 
     // component layout
@@ -506,6 +515,31 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         // insertion point of the Balmer edge: start of the per-walker edge-pixel search
         pd.edge_guess = (int)(std::lower_bound(d->wl, d->wl + P, d->balmer_edge) - d->wl);
     }
+    // walker parts: chunk boundary just blueward of the bluest Balmer edge the velocity-offset prior admits
+    pd.part_chunk = -1;
+    pd.part_stage0 = 0;
+    if (seen[SPAMM_COMP_BALMER] && pd.bc_on && pd.bpc_on && d->prior_lo && d->prior_hi) {
+        int o_bal = -1;
+        for (int q = 0; q < pd.n_comp; ++q) if (pd.comp_kind[q] == SPAMM_COMP_BALMER) o_bal = pd.comp_off[q];
+        const double lmax = std::max(std::fabs(d->prior_lo[o_bal + 3]), std::fabs(d->prior_hi[o_bal + 3]));
+        const double edge_min = d->balmer_edge * (1.0 - lmax / std::min(d->c_kms, d->c_cgs));
+        if (std::isfinite(edge_min)) {
+            const int i_min = (int)(std::lower_bound(d->wl, d->wl + P, edge_min) - d->wl) - 2;
+            const int pc = i_min / kChunk;
+            if (i_min > 0 && pc >= 1 && pc < pd.n_chunks) {
+                std::vector<int4> idx(P);
+                CUDA_TRY(cudaMemcpy(idx.data(), pd.bc_idx, (size_t)P * sizeof(int4), cudaMemcpyDeviceToHost));
+                int lo = pc * kChunk;
+                for (int i = pc * kChunk; i < P && i < pd.bc_nstage + kChunk; ++i)
+                    lo = std::min(lo, std::min(idx[i].x, idx[i].z));
+                pd.part_chunk = pc;
+                pd.part_stage0 = std::max(lo, 0) & ~1;
+                CUDA_TRY(cudaMalloc(&pl->d_part_chi, (size_t)pl->max_walkers * pd.n_chunks * sizeof(double)));
+                CUDA_TRY(cudaMalloc(&pl->d_part_cnt, (size_t)pl->max_walkers * sizeof(unsigned)));
+                CUDA_TRY(cudaMemset(pl->d_part_cnt, 0, (size_t)pl->max_walkers * sizeof(unsigned)));
+            }
+        }
+    }
 
     // exp_safe: inside the prior box every exp() argument of the fused kernel stays below 690 in
     // magnitude, so the FULL instantiation (ln-posterior only: out-of-prior walkers exit first) can
@@ -559,27 +593,27 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
     pl->smem_bytes = sizeof(WalkerCtx) + (size_t)(5 * pd.n_lines_pad + pd.n_chunks + pd.bc_nstage) * sizeof(double);
     if (pl->smem_bytes > 200 * 1024)
         return set_error(SPAMM_EINVAL, "spectrum has too many pixels blueward of the Balmer edge for the shared-memory stage");
-    const int sb = (int)pl->smem_bytes;
+    // The dynamic shared-memory limit is a per-function, process-wide attribute: never lower it (an
+    // earlier, larger plan may still be live), keep a high-water mark.
+    static int smem_high_water_dev[64] = {0};                 // per device
+    int& smem_high_water = smem_high_water_dev[dev_id & 63];
+    if ((int)pl->smem_bytes > smem_high_water) {
+        const int sb = (int)pl->smem_bytes;
 #define SPAMM_SMEM_ATTR(...) \
     CUDA_TRY(cudaFuncSetAttribute(k_walkers<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb))
-    SPAMM_SMEM_ATTR(0, true, false, 0); SPAMM_SMEM_ATTR(1, true, false, 0);
-    SPAMM_SMEM_ATTR(0, false, false, 0); SPAMM_SMEM_ATTR(1, false, false, 0);
-    SPAMM_SMEM_ATTR(0, true, true, 0); SPAMM_SMEM_ATTR(1, true, true, 0);
-    SPAMM_SMEM_ATTR(0, false, true, 0); SPAMM_SMEM_ATTR(1, false, true, 0);
-    SPAMM_SMEM_ATTR(0, true, false, 1); SPAMM_SMEM_ATTR(0, true, true, 1);
-    SPAMM_SMEM_ATTR(0, true, false, 3); SPAMM_SMEM_ATTR(0, true, true, 3);
-    SPAMM_SMEM_ATTR(0, true, false, 5); SPAMM_SMEM_ATTR(0, true, true, 5);
-    SPAMM_SMEM_ATTR(0, true, false, 7); SPAMM_SMEM_ATTR(0, true, true, 7);
-    SPAMM_SMEM_ATTR(0, true, false, 9); SPAMM_SMEM_ATTR(0, true, true, 9);
-    SPAMM_SMEM_ATTR(0, true, false, 11); SPAMM_SMEM_ATTR(0, true, true, 11);
-    SPAMM_SMEM_ATTR(0, true, false, 13); SPAMM_SMEM_ATTR(0, true, true, 13);
-    SPAMM_SMEM_ATTR(0, true, false, 15); SPAMM_SMEM_ATTR(0, true, true, 15);
-    SPAMM_SMEM_ATTR(0, true, false, 41); SPAMM_SMEM_ATTR(0, true, true, 41);
-    SPAMM_SMEM_ATTR(0, true, false, 73); SPAMM_SMEM_ATTR(0, true, true, 73);
-    SPAMM_SMEM_ATTR(0, true, false, 47); SPAMM_SMEM_ATTR(0, true, true, 47);
-    SPAMM_SMEM_ATTR(0, true, false, 79); SPAMM_SMEM_ATTR(0, true, true, 79);
-    SPAMM_SMEM_ATTR(0, true, false, 31); SPAMM_SMEM_ATTR(0, true, true, 31);
+        SPAMM_SMEM_ATTR(0, true, false, 0); SPAMM_SMEM_ATTR(1, true, false, 0);
+        SPAMM_SMEM_ATTR(0, false, false, 0); SPAMM_SMEM_ATTR(1, false, false, 0);
+        SPAMM_SMEM_ATTR(0, true, true, 0); SPAMM_SMEM_ATTR(1, true, true, 0);
+        SPAMM_SMEM_ATTR(0, false, true, 0); SPAMM_SMEM_ATTR(1, false, true, 0);
+#define SPAMM_SMEM_SPEC(S) SPAMM_SMEM_ATTR(0, true, false, S); SPAMM_SMEM_ATTR(0, true, true, S);
+        SPAMM_SPEC_LIST(SPAMM_SMEM_SPEC)
+#undef SPAMM_SMEM_SPEC
+#define SPAMM_SMEM_PARTS(S) SPAMM_SMEM_ATTR(0, true, false, S | kSpecParts);
+        SPAMM_PARTS_LIST(SPAMM_SMEM_PARTS)
+#undef SPAMM_SMEM_PARTS
 #undef SPAMM_SMEM_ATTR
+        smem_high_water = sb;
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     return SPAMM_OK;
 }
@@ -600,8 +634,8 @@ extern "C" int spamm_plan_bank_rows(const SpammPlan* pl) { return pl ? pl->bank_
 extern "C" int64_t spamm_plan_launch_count(const SpammPlan* pl) { return pl ? pl->launches : 0; }
 extern "C" int spamm_plan_set_walker_split(SpammPlan* pl, int32_t mode) {
     if (!pl) return set_error(SPAMM_EINVAL, "null plan");
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 4 && mode != 8)
-        return set_error(SPAMM_EINVAL, "walker split must be 0 (off), 1 (auto), 2, 4 or 8");
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 3 && mode != 4 && mode != 8)
+        return set_error(SPAMM_EINVAL, "walker split must be 0 (off), 1 (auto), 2, 4, 8 (cluster) or 3 (two parts)");
     pl->split_mode = mode;
     return SPAMM_OK;
 }
@@ -612,6 +646,43 @@ extern "C" int spamm_plan_status(SpammPlan* pl, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(&h, pl->dev.status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return h;
+}
+
+
+// The device status word is sticky (kernels only OR bits in).  A non-zero word means some walker needed a
+// table entry the plan does not hold and its ln-posterior is not the model's -- that must surface as an
+// error, never as a number.  A kernel that sets a bit also writes 1 to a mapped pinned host word, so the host
+// notices for free: synchronous entry points look at it after their synchronisation (check_status),
+// asynchronous ones at the start of the next call on the plan (deferred_status); spamm_plan_check does
+// the same on demand.  The details come from the device word.
+static int status_error(SpammPlan* pl, cudaStream_t st) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, pl->dev.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemsetAsync(pl->dev.status, 0, sizeof(int), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *reinterpret_cast<volatile int*>(pl->h_status) = 0;
+    if (h == 0) return SPAMM_OK;
+    std::string msg = "device status";
+    if (h & kStatSigmaRange) msg += ": a template width is outside the broadening bank (sigma_norm < 1 or beyond the prior's maximum)";
+    if (h & kStatBcKernel) msg += ": the Balmer-continuum log_conv kernel is wider than one pixel (unsupported grid/width)";
+    if (h & kStatBcStage) msg += ": the Balmer edge pixel lies beyond the staged continuum samples";
+    if (h & kStatPeerTimeout) msg += ": a peer rank's results did not arrive within 5 s (multi-GPU exchange)";
+    return set_error(SPAMM_ERANGE, msg);
+}
+
+static int deferred_status(SpammPlan* pl, cudaStream_t st) {
+    return *reinterpret_cast<volatile int*>(pl->h_status) ? status_error(pl, st) : SPAMM_OK;
+}
+
+// `st` was just synchronised
+static int check_status(SpammPlan* pl, cudaStream_t st) { return deferred_status(pl, st); }
+
+extern "C" int spamm_plan_check(SpammPlan* pl, void* stream) {
+    if (!pl) return set_error(SPAMM_EINVAL, "null plan");
+    const int h = spamm_plan_status(pl, stream);
+    if (h < 0) return h;
+    return h ? status_error(pl, (cudaStream_t)stream) : SPAMM_OK;
 }
 
 // direct-mode workspace (per-walker broadened rows), allocated on first use
@@ -675,6 +746,8 @@ template <int MODE, bool CANON, bool SPLIT, int SPEC = 0>
 static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
                       const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                       PeerOut po) {
+    // (SPEC & kSpecParts: csize = 2 independent CTAs per walker, red parts first; no cluster)
+    PartsWs pw{pl->d_part_chi, pl->d_part_cnt, n_walkers};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_walkers * csize), 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
@@ -686,17 +759,30 @@ static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, 
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     if (SPLIT) { cfg.attrs = &attr; cfg.numAttrs = 1; }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, SPEC>, pd, params_dev, w0, out_dev, mask, dr, po));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, SPEC>, pd, params_dev, w0, out_dev, mask, dr, po, pw));
     return SPAMM_OK;
 }
 
 static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
-    if (pl->split_mode == 0) return 1;
+    if (pl->split_mode == 0 || pl->split_mode == 3) return 1;
     int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
     int c = 1;
     while (c < 8 && n_walkers * c * 4 <= slots) c *= 2;       // keep the split grid within half the slots
     if (pl->split_mode > 1) c = pl->split_mode;          // forced (tests)
     return c;
+}
+
+// Two independent CTAs per walker (kSpecParts)?  Forced by split mode 3; automatic for ensembles of a few
+// waves of CTAs, where halving the work items shortens the tail of the last wave.
+static bool parts_for(const SpammPlan* pl, const PlanDev& pd, int n_walkers) {
+    if (pd.part_chunk < 0 || !pl->d_part_chi || n_walkers > pl->max_walkers) return false;
+    if (pl->split_mode == 3) return true;
+    if (pl->split_mode != 1) return false;
+    // measured on B200 (profiles/r02_split_table.txt): ahead of one CTA per walker from about half a wave of
+    // CTAs (the two parts of a walker can land on different SMs) up to about a wave and a half
+    const int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
+    const int hi = pl->parts_max_walkers > 0 ? pl->parts_max_walkers : 3 * slots / 2;
+    return 2 * n_walkers > slots && n_walkers <= hi;
 }
 
 // Which specialised instantiation (SPEC bit set, 0 = none) serves ln-posterior calls on this plan
@@ -735,15 +821,23 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                     PeerOut po) {
     const int c = cluster_size_for(pl, n_walkers);
+    if (MODE == 0 && c == 1 && parts_for(pl, pd, n_walkers)) {
+#define SPAMM_LAUNCH_PARTS(S)                                                                                    \
+    case S:                                                                                                      \
+        return launch_one<0, true, false, S | kSpecParts>(pl, n_walkers, 2, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        switch (spec_of(pl, pd, mask, dr)) {
+            SPAMM_PARTS_LIST(SPAMM_LAUNCH_PARTS)
+            default: break;
+        }
+#undef SPAMM_LAUNCH_PARTS
+    }
     if (MODE == 0) {
 #define SPAMM_LAUNCH_SPEC(S)                                                                                     \
     case S:                                                                                                      \
         return c > 1 ? launch_one<0, true, true, S>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po) \
                      : launch_one<0, true, false, S>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
         switch (spec_of(pl, pd, mask, dr)) {
-            SPAMM_LAUNCH_SPEC(1) SPAMM_LAUNCH_SPEC(3) SPAMM_LAUNCH_SPEC(5) SPAMM_LAUNCH_SPEC(7) SPAMM_LAUNCH_SPEC(9)
-            SPAMM_LAUNCH_SPEC(11) SPAMM_LAUNCH_SPEC(13) SPAMM_LAUNCH_SPEC(15) SPAMM_LAUNCH_SPEC(31)
-            SPAMM_LAUNCH_SPEC(41) SPAMM_LAUNCH_SPEC(73) SPAMM_LAUNCH_SPEC(47) SPAMM_LAUNCH_SPEC(79)
+            SPAMM_SPEC_LIST(SPAMM_LAUNCH_SPEC)
             default: break;
         }
 #undef SPAMM_LAUNCH_SPEC
@@ -759,7 +853,7 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
 template <int MODE>
 static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
                           double* out_dev, cudaStream_t st, bool force_direct,
-                          PeerOut po = PeerOut{nullptr, 0, 0}) {
+                          PeerOut po = PeerOut{nullptr, 0, 0, nullptr, 0u, 0, 0ull}) {
     const PlanDev& pd = pl->dev;
     bool need_fe = false, need_host = false;
     for (int q = 0; q < pd.n_comp; ++q) {
@@ -803,6 +897,8 @@ extern "C" int spamm_lnpost_batch(SpammPlan* pl, const double* params_dev, int32
     if (n_walkers < 0) return set_error(SPAMM_EINVAL, "negative walker count");
     if (n_walkers == 0) return SPAMM_OK;
     if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    int rc = deferred_status(pl, (cudaStream_t)stream);
+    if (rc) return rc;
     return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, lnp_dev, (cudaStream_t)stream, false);
 }
 
@@ -813,7 +909,8 @@ extern "C" int spamm_lnpost_batch_p2p(SpammPlan* pl, const double* params_dev, i
     if (n_walkers < 0 || n_peers < 1 || elem_offset < 0) return set_error(SPAMM_EINVAL, "bad argument");
     if (n_walkers == 0) return SPAMM_OK;
     if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
-    PeerOut po{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), n_peers, (long long)elem_offset};
+    PeerOut po{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), n_peers, (long long)elem_offset,
+               nullptr, 0u, 0, 0ull};
     return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, nullptr, (cudaStream_t)stream, false, po);
 }
 
@@ -852,6 +949,7 @@ extern "C" int spamm_lnpost_batch_host(SpammPlan* pl, const double* params_host,
         CUDA_TRY(cudaMemcpyAsync(dst, pl->d_lnp, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         if (!pin_out) memcpy(lnp_host + w0, pl->h_lnp, (size_t)nW * sizeof(double));
+        if ((rc = check_status(pl, st))) return rc;
     }
     return SPAMM_OK;
 }
@@ -926,7 +1024,7 @@ extern "C" int spamm_stretch_accept(double* walkers_dev, double* lnp_dev, int32_
     int Ns = K / 2;
     k_stretch_accept<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed, iteration,
-        reinterpret_cast<long long*>(naccepted_dev));
+        reinterpret_cast<long long*>(naccepted_dev), nullptr, 0, 0ull, nullptr, nullptr);
     CUDA_TRY(cudaGetLastError());
     return SPAMM_OK;
 }
@@ -973,6 +1071,267 @@ extern "C" int spamm_stretch_run(SpammPlan* pl, double* walkers_dev, double* lnp
     }
     return SPAMM_OK;
 }
+
+// ---------------------------------------------------------------------------
+// multi-GPU: walker shards, results exchanged by the compute kernel itself
+// ---------------------------------------------------------------------------
+// Region of one rank (device memory, mapped into every peer by CUDA IPC or handed in as raw pointers):
+//   words [0, kFlagWords)                       flag block, word r = last epoch rank r has completed
+//   words [kFlagWords, kFlagWords + max_n)      result buffer of even epochs
+//   words [kFlagWords + max_n, ... + 2 max_n)   result buffer of odd epochs
+// Two buffers suffice: a rank can start epoch e + 2 only after it has seen every peer's flag for e + 1, which
+// a peer raises after (in stream order) it consumed the results of epoch e.
+struct SpammExchange {
+    int n_ranks = 1, rank = 0;
+    int64_t max_n = 0;
+    uint64_t epoch = 0;                    // identical on every rank: all ranks make the same calls
+    void* region = nullptr;                // this rank's region (cudaMalloc)
+    std::vector<void*> peer;               // every rank's region as mapped here (peer[rank] == region)
+    std::vector<bool> opened;              // opened through cudaIpcOpenMemHandle
+    unsigned long long* d_peer_ptrs = nullptr;   // device copy of `peer`
+    unsigned* d_done = nullptr;            // retired-walker counter of the running call
+    bool connected = false;
+    // staging of the *_host entry point
+    double *h_params = nullptr, *h_lnp = nullptr, *d_params = nullptr;
+    cudaStream_t own_stream = nullptr;
+};
+
+extern "C" void spamm_shard_bounds(int64_t n, int32_t n_ranks, int32_t rank, int64_t* lo, int64_t* hi) {
+    const int64_t per = n_ranks > 0 ? (n + n_ranks - 1) / n_ranks : n;
+    const int64_t a = std::min<int64_t>((int64_t)rank * per, n);
+    if (lo) *lo = a;
+    if (hi) *hi = std::min<int64_t>(a + per, n);
+}
+
+extern "C" int64_t spamm_exchange_region_bytes(int64_t max_walkers) {
+    return (int64_t)sizeof(double) * (kFlagWords + 2 * max_walkers);
+}
+
+extern "C" void spamm_exchange_destroy(SpammExchange* ex) {
+    if (!ex) return;
+    for (size_t r = 0; r < ex->peer.size(); ++r)
+        if (ex->opened[r] && ex->peer[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+    cudaFree(ex->region); cudaFree(ex->d_peer_ptrs); cudaFree(ex->d_done); cudaFree(ex->d_params);
+    if (ex->h_params) cudaFreeHost(ex->h_params);
+    if (ex->h_lnp) cudaFreeHost(ex->h_lnp);
+    if (ex->own_stream) cudaStreamDestroy(ex->own_stream);
+    delete ex;
+}
+
+static int exchange_create_impl(SpammExchange* ex, int32_t n_ranks, int32_t rank, int64_t max_walkers,
+                                void* ipc_handle_out) {
+    if (n_ranks < 1 || n_ranks > kFlagWords || rank < 0 || rank >= n_ranks || max_walkers < 1)
+        return set_error(SPAMM_EINVAL, "exchange: need 1 <= n_ranks <= 64, 0 <= rank < n_ranks, max_walkers >= 1");
+    ex->n_ranks = n_ranks; ex->rank = rank; ex->max_n = max_walkers;
+    const size_t bytes = (size_t)spamm_exchange_region_bytes(max_walkers);
+    CUDA_TRY(cudaMalloc(&ex->region, bytes));
+    CUDA_TRY(cudaMemset(ex->region, 0, bytes));
+    CUDA_TRY(cudaMalloc(&ex->d_done, sizeof(unsigned)));
+    CUDA_TRY(cudaMemset(ex->d_done, 0, sizeof(unsigned)));
+    CUDA_TRY(cudaMalloc(&ex->d_peer_ptrs, (size_t)n_ranks * sizeof(unsigned long long)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    ex->peer.assign(n_ranks, nullptr);
+    ex->opened.assign(n_ranks, false);
+    ex->peer[rank] = ex->region;
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "SPAMM_IPC_HANDLE_BYTES");
+        cudaIpcMemHandle_t h;
+        CUDA_TRY(cudaIpcGetMemHandle(&h, ex->region));
+        memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    // Load every kernel of the exchange path now: with lazy module loading the first launch of a kernel
+    // can wait for running kernels to drain -- and a consumer spinning on a peer's flag never drains if
+    // that peer (another stream of this process) is the one stuck loading.
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_raise_flags));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_wait_flags));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_stretch_propose));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_stretch_accept));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_chain_record));
+    if (n_ranks == 1) {
+        unsigned long long p = (unsigned long long)ex->region;
+        CUDA_TRY(cudaMemcpy(ex->d_peer_ptrs, &p, sizeof(p), cudaMemcpyHostToDevice));
+        ex->connected = true;
+    }
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_exchange_create(int32_t n_ranks, int32_t rank, int64_t max_walkers, SpammExchange** out,
+                                     void* ipc_handle_out) {
+    if (!out) return set_error(SPAMM_EINVAL, "null argument");
+    SpammExchange* ex = new SpammExchange();
+    int rc = exchange_create_impl(ex, n_ranks, rank, max_walkers, ipc_handle_out);
+    if (rc) { spamm_exchange_destroy(ex); *out = nullptr; return rc; }
+    *out = ex;
+    return SPAMM_OK;
+}
+
+static int exchange_finish_connect(SpammExchange* ex) {
+    std::vector<unsigned long long> p(ex->n_ranks);
+    for (int r = 0; r < ex->n_ranks; ++r) p[r] = (unsigned long long)ex->peer[r];
+    CUDA_TRY(cudaMemcpy(ex->d_peer_ptrs, p.data(), p.size() * sizeof(p[0]), cudaMemcpyHostToDevice));
+    ex->connected = true;
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_exchange_connect(SpammExchange* ex, const void* all_handles) {
+    if (!ex || !all_handles) return set_error(SPAMM_EINVAL, "null argument");
+    const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+    for (int r = 0; r < ex->n_ranks; ++r) {
+        if (r == ex->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + r, sizeof(h));
+        void* p = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peer[r] = p;
+        ex->opened[r] = true;
+    }
+    return exchange_finish_connect(ex);
+}
+
+extern "C" int spamm_exchange_connect_ptrs(SpammExchange* ex, const uint64_t* region_ptrs) {
+    if (!ex || !region_ptrs) return set_error(SPAMM_EINVAL, "null argument");
+    for (int r = 0; r < ex->n_ranks; ++r)
+        if (r != ex->rank) ex->peer[r] = reinterpret_cast<void*>(region_ptrs[r]);
+    return exchange_finish_connect(ex);
+}
+
+extern "C" uint64_t spamm_exchange_region_ptr(const SpammExchange* ex) { return ex ? (uint64_t)ex->region : 0; }
+extern "C" uint64_t spamm_exchange_epoch(const SpammExchange* ex) { return ex ? ex->epoch : 0; }
+
+// queue one sharded evaluation of params_dev[n_total][D]: this rank's slice through k_walkers with P2P stores
+// and the flag raise; returns the epoch's buffer in this rank's region (complete once every flag >= epoch)
+static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_dev, int32_t n_total,
+                        cudaStream_t st, const double** buf_out, uint64_t* epoch_out) {
+    if (!ex->connected) return set_error(SPAMM_EINVAL, "exchange is not connected");
+    if (n_total > ex->max_n) return set_error(SPAMM_EINVAL, "exchange region holds fewer walkers than n_total");
+    const uint64_t e = ++ex->epoch;
+    int64_t lo, hi;
+    spamm_shard_bounds(n_total, ex->n_ranks, ex->rank, &lo, &hi);
+    const long long boff = kFlagWords + (long long)(e & 1) * ex->max_n;
+    PeerOut po{ex->d_peer_ptrs, ex->n_ranks, boff + lo, ex->d_done, (unsigned)(hi - lo), ex->rank, e};
+    if (hi > lo) {
+        int rc = launch_walkers<0>(pl, full_mask(pl), params_dev + (size_t)lo * pl->dev.D, (int)(hi - lo), nullptr, st,
+                                   false, po);
+        if (rc) return rc;
+    } else {
+        k_raise_flags<<<1, 1, 0, st>>>(po);
+        pl->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+    }
+    *buf_out = reinterpret_cast<const double*>(ex->region) + boff;
+    *epoch_out = e;
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_lnpost_batch_sharded(SpammPlan* pl, SpammExchange* ex, const double* params_dev,
+                                          int32_t n_total, double* lnp_dev, const double** lnp_region_out,
+                                          void* stream) {
+    if (!pl || !ex || !params_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_total < 1) return set_error(SPAMM_EINVAL, "need at least one walker");
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* buf = nullptr;
+    uint64_t e = 0;
+    int rc = deferred_status(pl, st);
+    if (rc) return rc;
+    if ((rc = sharded_eval(pl, ex, params_dev, n_total, st, &buf, &e))) return rc;
+    k_wait_flags<<<1, kFlagWords, 0, st>>>(reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e,
+                                           pl->dev.status, pl->dev.status_host);
+    pl->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (lnp_dev) CUDA_TRY(cudaMemcpyAsync(lnp_dev, buf, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (lnp_region_out) *lnp_region_out = buf;
+    return SPAMM_OK;
+}
+
+extern "C" int spamm_lnpost_batch_sharded_host(SpammPlan* pl, SpammExchange* ex, const double* params_host,
+                                               int32_t n_total, double* lnp_host) {
+    if (!pl || !ex || !params_host || !lnp_host) return set_error(SPAMM_EINVAL, "null argument");
+    if (n_total < 1 || n_total > ex->max_n) return set_error(SPAMM_EINVAL, "walker count outside the exchange region");
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    const int D = pl->dev.D;
+    if (!ex->own_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ex->own_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaMallocHost(&ex->h_params, (size_t)ex->max_n * D * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&ex->h_lnp, (size_t)ex->max_n * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&ex->d_params, (size_t)ex->max_n * D * sizeof(double)));
+    }
+    cudaStream_t st = ex->own_stream;
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    // only this rank's slice of the parameters travels to the device; the whole result vector travels back
+    int64_t lo, hi;
+    spamm_shard_bounds(n_total, ex->n_ranks, ex->rank, &lo, &hi);
+    if (hi > lo) {
+        const size_t nb = (size_t)(hi - lo) * D * sizeof(double);
+        const double* src = params_host + (size_t)lo * D;
+        if (!is_pinned(params_host)) { memcpy(ex->h_params, src, nb); src = ex->h_params; }
+        CUDA_TRY(cudaMemcpyAsync(ex->d_params + (size_t)lo * D, src, nb, cudaMemcpyHostToDevice, st));
+    }
+    const double* buf = nullptr;
+    uint64_t e = 0;
+    int rc = sharded_eval(pl, ex, ex->d_params, n_total, st, &buf, &e);
+    if (rc) return rc;
+    k_wait_flags<<<1, kFlagWords, 0, st>>>(reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e,
+                                           pl->dev.status, pl->dev.status_host);
+    pl->launches += 1;
+    const bool pin_out = is_pinned(lnp_host);
+    double* dst = pin_out ? lnp_host : ex->h_lnp;
+    CUDA_TRY(cudaMemcpyAsync(dst, buf, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!pin_out) memcpy(lnp_host, ex->h_lnp, (size_t)n_total * sizeof(double));
+    return check_status(pl, st);
+}
+
+// spamm_stretch_run with the walkers of every half-step sharded over the ranks of an exchange: every rank
+// holds the replicated state and the same counter-based RNG, proposes the whole half-ensemble, evaluates its
+// slice (results stored into every rank's region by the kernel) and accepts after the flag wait fused into
+// k_stretch_accept -- no host code and no collective per half-step.
+extern "C" int spamm_stretch_run_sharded(SpammPlan* pl, SpammExchange* ex, double* walkers_dev, double* lnp_dev,
+                                         int32_t K, double a, uint64_t seed, uint64_t iter0, int32_t n_iter,
+                                         double* q_dev, double* z_dev, int64_t* naccepted_dev, double* chain_dev,
+                                         double* lnp_chain_dev, int64_t chain_len, void* stream) {
+    if (!pl || !ex || !walkers_dev || !lnp_dev || !q_dev || !z_dev) return set_error(SPAMM_EINVAL, "null argument");
+    if (K < 2 || (K & 1) || n_iter < 0) return set_error(SPAMM_EINVAL, "need an even walker count");
+    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
+    if ((chain_dev || lnp_chain_dev) && (int64_t)iter0 + n_iter > chain_len)
+        return set_error(SPAMM_EINVAL, "chain buffer too short");
+    const int D = pl->dev.D, Ns = K / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int it = 0; it < n_iter; ++it) {
+        const uint64_t iteration = iter0 + (uint64_t)it;
+        for (int half = 0; half < 2; ++half) {
+            int rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream);
+            if (rc) return rc;
+            const double* buf = nullptr;
+            uint64_t e = 0;
+            if ((rc = sharded_eval(pl, ex, q_dev, Ns, st, &buf, &e))) return rc;
+            k_stretch_accept<<<(Ns + 127) / 128, 128, 0, st>>>(
+                walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, buf, seed, iteration,
+                reinterpret_cast<long long*>(naccepted_dev),
+                reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e, pl->dev.status,
+                pl->dev.status_host);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (chain_dev || lnp_chain_dev) {
+            int rc = spamm_chain_record(walkers_dev, lnp_dev, K, D, (int64_t)iteration, chain_len, chain_dev,
+                                        lnp_chain_dev, stream);
+            if (rc) return rc;
+        }
+    }
+    return SPAMM_OK;
+}
+
+#ifdef SPAMM_TRACE
+extern "C" int spamm_debug_set_trace(unsigned long long* buf) {
+    CUDA_TRY(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
+    return SPAMM_OK;
+}
+#endif
 
 extern "C" int spamm_fp64_peak_probe(int32_t iters, int32_t repeats, double* tflops_out) {
     if (!tflops_out || iters < 1 || repeats < 1) return set_error(SPAMM_EINVAL, "bad argument");

@@ -22,18 +22,87 @@ struct TemplCoef {
 
 // Multi-GPU result exchange fused into the kernel: instead of writing lnp[w] locally and
 // all-gathering afterwards, the finishing thread stores the value straight into every peer's
-// symmetric buffer over NVLink (P2P stores); bufs == nullptr selects the plain local store.
+// region over NVLink (P2P stores); bufs == nullptr selects the plain local store.
+// With done_cnt set the kernel also signals: the CTA that retires the launch's last walker raises
+// this rank's flag (word `rank` of every peer's flag block, value `epoch`) after a system-scope
+// fence, so a consumer on any rank that has seen flag >= epoch (k_wait_flags, k_stretch_accept) sees
+// all of this rank's results -- no host-side barrier, no collective.
 struct PeerOut {
     const unsigned long long* bufs;   // device array of n_peers base pointers (incl. this rank)
     int n_peers;
-    long long offset;                 // element offset of this launch's walker 0 in the gathered vector
+    long long offset;                 // element offset of this launch's walker 0 from a base pointer
+    unsigned* done_cnt;               // device counter of retired walkers (null: no signalling)
+    unsigned n_done;                  // walkers of the whole sharded call (may span several launches)
+    int rank;                         // this rank's flag word
+    unsigned long long epoch;         // value to raise
 };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// raise this rank's flag in every peer's flag block (the first kFlagWords words of a region)
+__device__ __forceinline__ void raise_flags(const PeerOut& po) {
+    __threadfence_system();
+    for (int r = 0; r < po.n_peers; ++r)
+        st_release_sys(reinterpret_cast<unsigned long long*>(po.bufs[r]) + po.rank, po.epoch);
+}
 
 __device__ __forceinline__ void store_result(double* out, int w, double v, const PeerOut& po) {
     if (po.bufs == nullptr) { out[w] = v; return; }
     for (int r = 0; r < po.n_peers; ++r)
         reinterpret_cast<double*>(po.bufs[r])[po.offset + w] = v;
+    if (po.done_cnt != nullptr) {
+        __threadfence_system();                                   // results before the count
+        if (atomicAdd(po.done_cnt, 1u) + 1u == po.n_done) {       // this walker retires the call
+            *po.done_cnt = 0u;
+            raise_flags(po);
+        }
+    }
 }
+
+// a rank without walkers in a sharded call still has to raise its flag
+__global__ void k_raise_flags(PeerOut po) { raise_flags(po); }
+
+// Spin until every rank's flag in this rank's flag block has reached `epoch` (threads 0..n_peers-1 of the
+// calling block); gives up after ~5 s and sets kStatPeerTimeout so a lost peer cannot hang the device.
+__device__ __forceinline__ void wait_flags(const unsigned long long* flags, int n_peers, unsigned long long epoch,
+                                           int* status, int* status_host) {
+    if ((int)threadIdx.x < n_peers) {
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+            if ((++spins & 1023u) == 0u) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 5000000000ull) { flag_status(status, status_host, kStatPeerTimeout); break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void k_wait_flags(const unsigned long long* flags, int n_peers, unsigned long long epoch, int* status,
+                             int* status_host) {
+    wait_flags(flags, n_peers, epoch, status, status_host);
+}
+
+// Walker PARTS (kSpecParts instantiations): a walker is evaluated by two independent CTAs -- the "red" part
+// takes the 64-pixel chunks from PlanDev::part_chunk (just blueward of the Balmer edge) on and builds the line
+// table and cluster moments, the "blue" part takes the chunks before it and stages the Balmer continuum -- so
+// neither repeats the other's share of the prologue.  Each part leaves its per-chunk chi^2 partials in `chi`;
+// the part that finishes second sums all of them in the unsplit kernel's fixed order (bit-identical result).
+struct PartsWs {
+    double* chi;           // [n_walkers][n_chunks]
+    unsigned* cnt;         // [n_walkers], zero between launches
+    int n_walkers;         // blocks [0, n) are the red parts, [n, 2n) the blue parts
+};
 
 // Storey & Hummer table look-up: kx=ky=1 FITPACK spline == clamped bilinear
 __device__ double sh95_bilinear(const PlanDev& pl, int k, double n_e, double T) {
@@ -125,6 +194,8 @@ struct alignas(16) WalkerCtx {   // shared-memory block, one per CTA
     int bc_istar, bpc_istar;
     int prior_ok;
     int bc_finite;       // bc_scale is finite: chunks without Balmer-continuum pixels may skip the 0 * scale
+    int task_next;       // PARTS: next task of the CTA's dynamic deal
+    int pad_;
 };
 static_assert(sizeof(WalkerCtx) % 16 == 0, "line table must stay 16-byte aligned");
 
@@ -315,6 +386,25 @@ __device__ __forceinline__ int series_terms(double As, double cmin) {
 #ifndef SPAMM_MIN_BLOCKS
 #define SPAMM_MIN_BLOCKS 4
 #endif
+// kernel-iteration builds (-DSPAMM_TRACE): per-CTA phase time stamps, read back by tools/trace_ctas.py
+#ifdef SPAMM_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int slot) {
+    if (threadIdx.x == 0 && g_trace != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_trace[(size_t)blockIdx.x * 8 + slot] = t;
+        if (slot == 0) {
+            unsigned sm;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+            g_trace[(size_t)blockIdx.x * 8 + 7] = sm;
+        }
+    }
+}
+#define SPAMM_MARK(slot) trace_mark(slot)
+#else
+#define SPAMM_MARK(slot)
+#endif
 constexpr int kChunk = 32 * kPix;      // pixels per warp task
 
 // MODE 0: ln-posterior, 1: model flux out.  CANON: the live components are in the reference's
@@ -334,13 +424,31 @@ constexpr int kSpecNc = 1, kSpecFe = 2, kSpecHost = 4, kSpecBalmer = 8, kSpecExt
 // modifiers of kSpecBalmer: BalmerCombined with one part switched off -- run_spamm's "BC" without "BPC" is the
 // continuum alone (run_spamm.py:118-121; the reference's own examples/test_spamm.py fits that model)
 constexpr int kSpecNoBpc = 32, kSpecNoBc = 64;
+// launch-shape modifier: one walker = a red-part CTA + a blue-part CTA (PartsWs); full Balmer models only
+constexpr int kSpecParts = 128;
 // NC | NC+Fe | NC+host | NC+Fe+host | NC+Balmer | NC+Fe+Balmer | NC+host+Balmer | full | full+Extinction |
 // NC+Balmer and full with the continuum only / the lines only
-constexpr int kSpecs[] = {1, 3, 5, 7, 9, 11, 13, 15, 31, 9 | kSpecNoBpc, 9 | kSpecNoBc, 15 | kSpecNoBpc, 15 | kSpecNoBc};
-template <int MODE, bool CANON, bool SPLIT, int SPEC>
+// (SPAMM_DEV_BUILD: kernel-iteration builds compile the config-5 instantiation only)
+#ifdef SPAMM_DEV_BUILD
+#define SPAMM_SPEC_LIST(X) X(15)
+#define SPAMM_PARTS_LIST(X) X(15)
+#else
+#define SPAMM_PARTS_LIST(X) X(9) X(11) X(13) X(15) X(31)     // models with both Balmer parts
+#define SPAMM_SPEC_LIST(X) X(1) X(3) X(5) X(7) X(9) X(11) X(13) X(15) X(31) X(41) X(73) X(47) X(79)
+#endif
+#define SPAMM_SPEC_ENTRY(S) S,
+constexpr int kSpecs[] = {SPAMM_SPEC_LIST(SPAMM_SPEC_ENTRY)};
+#undef SPAMM_SPEC_ENTRY
+static_assert((9 | kSpecNoBpc) == 41 && (9 | kSpecNoBc) == 73 && (15 | kSpecNoBpc) == 47 && (15 | kSpecNoBc) == 79,
+              "SPAMM_SPEC_LIST spells the Balmer-part modifiers as numbers");
+template <int MODE, bool CANON, bool SPLIT, int SPECP>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
-          uint32_t mask, DirectRows dr, PeerOut po) {
+          uint32_t mask, DirectRows dr, PeerOut po, PartsWs pw) {
+    constexpr int SPEC = SPECP & ~kSpecParts;
+    constexpr bool PARTS = (SPECP & kSpecParts) != 0;
+    static_assert(!PARTS || (!SPLIT && MODE == 0 && (SPEC & kSpecBalmer) && !(SPEC & (kSpecNoBpc | kSpecNoBc))),
+                  "walker parts: ln-posterior of a specialised model with both Balmer parts, no cluster split");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WalkerCtx& c = *reinterpret_cast<WalkerCtx*>(smem_raw);
     double* sLine = reinterpret_cast<double*>(smem_raw + sizeof(WalkerCtx));   // [n_pad/4][12] grouped
@@ -350,16 +458,25 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     double* sF0 = sChi + pl.n_chunks;                                           // [bc_nstage]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SPAMM_MARK(0);
     int csize = 1, crank = 0;
     if (SPLIT) {
         cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
         csize = (int)cl.num_blocks();
         crank = (int)cl.block_rank();
     }
-    const int wloc = SPLIT ? blockIdx.x / csize : blockIdx.x;   // walker within this launch
+    int wloc = SPLIT ? blockIdx.x / csize : blockIdx.x;   // walker within this launch
+    // PARTS: is_red builds the line table / moments and owns chunks >= part_chunk, is_blue stages the whole
+    // Balmer continuum and owns the chunks before it (both true: the whole walker in one CTA)
+    bool is_red = true, is_blue = true;
+    if (PARTS) {
+        is_red = (int)blockIdx.x < pw.n_walkers;
+        is_blue = !is_red;
+        if (is_blue) wloc -= pw.n_walkers;
+    }
     const int w = w0 + wloc;
     const int P = pl.P;
-    const double* pw = params + (size_t)w * pl.D;
+    const double* pwalk = params + (size_t)w * pl.D;
 
     // The first CTAs stream the template bank into L2 (it is demand-fetched row by row otherwise:
     // ~20 us on a cold L2, i.e. after another kernel evicted it)
@@ -379,10 +496,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         }
     }
     // ---- P0: parameters + flat-box prior (Model.prior, Model.py:449-470) -----------------
-    if (tid == 0) c.prior_ok = 1;
+    if (tid == 0) { c.prior_ok = 1; c.task_next = 0; }
     __syncthreads();
     if (tid < pl.D) {
-        double v = pw[tid];
+        double v = pwalk[tid];
         c.p[tid] = v;
 
         if (MODE == 0 && pl.lo != nullptr) {
@@ -391,10 +508,11 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     __syncthreads();
     if (MODE == 0 && !c.prior_ok) {       // ln_posterior returns -inf before any flux (Model.py:67-69)
-        if (tid == 0 && crank == 0) store_result(out, w, -CUDART_INF, po);
+        if (tid == 0 && crank == 0 && is_red) store_result(out, w, -CUDART_INF, po);
         return;
     }
 
+    SPAMM_MARK(1);
     // ---- which components are live ------------------------------------------------------
     int off_nc = -1, off_bal = -1, q_bal = pl.n_comp;
     bool has_fe = false, has_host = false;
@@ -462,7 +580,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double sn = sigma_norm_of(ts, t, c.p[ts.param_off + ts.n_templ]);
             int sig = 1;
             if (sn >= 1.0 && sn <= (double)ts.bank_sig_max[t]) sig = (int)sn;
-            else { atomicOr(pl.status, kStatSigmaRange); norm = CUDART_NAN; }
+            else { flag_status(pl.status, pl.status_host, kStatSigmaRange); norm = CUDART_NAN; }
             int row = ts.bank_row0[t] + sig - 1;
             f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
         }
@@ -481,7 +599,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double sn = sigma_norm_of(ts, t, c.p[ts.param_off + ts.n_templ]);
             int sig = 1;
             if (sn >= 1.0 && sn <= (double)ts.bank_sig_max[t]) sig = (int)sn;
-            else { atomicOr(pl.status, kStatSigmaRange); norm = CUDART_NAN; }
+            else { flag_status(pl.status, pl.status_host, kStatSigmaRange); norm = CUDART_NAN; }
             int row = ts.bank_row0[t] + sig - 1;
             f = ts.bank_f + (size_t)row * P; nf = ts.bank_nf[row];
         }
@@ -497,9 +615,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             c.bc_istar = is;
             // log_conv kernel: kernel_width = round(5*dpix) must be 0          BC:229-233
             double dpix = (b_lwid / pl.c_cgs) / pl.bc_dlnew;
-            if (rint(5 * dpix) != 0.0) atomicOr(pl.status, kStatBcKernel);
+            if (rint(5 * dpix) != 0.0) flag_status(pl.status, pl.status_host, kStatBcKernel);
             const int4 kk = pl.bc_idx[is];
-            if (max(kk.y, kk.w) >= pl.bc_nstage) atomicOr(pl.status, kStatBcStage);
+            // (reported as an error by the host; no Balmer-continuum pixel is evaluated so nothing reads past the stage)
+            if (max(kk.y, kk.w) >= pl.bc_nstage) { flag_status(pl.status, pl.status_host, kStatBcStage); c.bc_istar = -1; }
         }
     }
     if (warp == 4 % kNW && lane == 0) {
@@ -509,7 +628,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             c.bpc_istar = nearest_index_guess(pl.wl, P, edge_wl, pl.edge_guess);   // BC:382
         }
     }
-    if (do_bpc) {
+    if (do_bpc && is_red) {
         const double shift = bal_shift, width = bal_width;
         const double inv_kT_l = 1.0 / kT;
         // BC:376; only the SH95 look-ups (n <= 50, the first threads) use it
@@ -537,7 +656,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         const double inv_kT = 1.0 / kT;
         if (FULL && pl.bc_pair_ok && pl.bc_dhnu_max * inv_kT <= 0.01) {
             // adjacent pixel pairs, one pair per trip, the next pair's loads issued before this pair's arithmetic
-            int k = 2 * tid;
+            // (a red part needs the samples under its own Balmer-continuum pixels and the normaliser only)
+            int k = (PARTS && is_red ? pl.part_stage0 : 0) + 2 * tid;
             double2 h, kk, t3;
             if (k < nst) {
                 h = *reinterpret_cast<const double2*>(pl.bc_hnu + k);
@@ -558,7 +678,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
         } else {
             // one pixel per trip, the next pixel's loads issued before this pixel's arithmetic
-            int k = tid;
+            int k = (PARTS && is_red ? pl.part_stage0 : 0) + tid;
             double h = 0.0, kk = 0.0, t3 = 0.0;
             if (k < nst) { h = pl.bc_hnu[k]; kk = pl.bc_K[k]; t3 = pl.bc_t3[k]; }
 #pragma unroll 1
@@ -572,17 +692,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     }
     __syncthreads();
 
+    SPAMM_MARK(2);
     // (the ratio recursion flux_ratios[i] = flux_ratios[i-1] * exp(e_i / kT), BC:292-296, is telescoped:
     //  r_n = r_50 * exp(sum_{m=51..n} e_m / kT); line_cum holds the partial sums, P3 applies r_50)
     // ---- P3: finish the line table; BC and BpC normalisers; cluster moments -------------------------
     const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
     double bpc_scale = 0.0;
     if (do_bc && warp == kNW - 1 && lane == 0) {
-        double fnorm = bc_conv_at(pl, sF0, bc_istar);                    // BC:444
+        double fnorm = bc_istar >= 0 ? bc_conv_at(pl, sF0, bc_istar) : CUDART_NAN;     // BC:444
         c.bc_scale = b_norm / fnorm;                                     // BC:446
         c.bc_finite = isfinite(c.bc_scale) ? 1 : 0;
     }
-    if (do_bpc) {
+    if (do_bpc && is_red) {
         const int n50 = min(max(51 - pl.line_min, 0), n_lines);       // first line with n > 50
         const double r50 = n50 > 0 ? sG[n50 - 1] : 0.0;               // flux_ratios[-1] of a zeroed array
         // line table entries (w^2, a = ratio * w) and, on the way, the BpC normaliser = the line sum
@@ -673,11 +794,14 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         }
     }
     __syncthreads();
-    if (do_bpc) {
+    if (do_bpc && is_red) {
         double tot = 0.0;
         for (int q = 0; q < kThreads / 32; ++q) tot += c.red[q];
         bpc_scale = b_norm / tot;                                        // BC:387
     }
+    // (a blue part holds no pixel beyond the Balmer edge: its pseudo-continuum term is 0 * bpc_scale = 0,
+    //  bpc_scale being positive and finite inside the prior box of a specialised model)
+    SPAMM_MARK(3);
     const double bc_scale = c.bc_scale;
     const bool bc_finite = c.bc_finite != 0;
     double* fout = (MODE == 1) ? out + (size_t)wloc * P : nullptr;
@@ -690,8 +814,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // a plain atom.shared into its warp-aggregation sequence -- and measured 2.7 % slower, 1 % slower
     // when tasks are fetched in pairs, although the one task inside the line forest, ~13x the work of
     // the others, leaves its warp behind: the SM's other CTAs fill the gap.)
-    for (int t = SPLIT ? warp * csize + crank : warp; t < n_chunks; t += (kThreads / 32) * csize) {
-        const int chunk = n_chunks - 1 - t;
+    const int chunk_top = PARTS && is_blue ? pl.part_chunk : n_chunks;        // this CTA owns chunks
+    const int chunk_bot = PARTS && is_red ? pl.part_chunk : 0;                //   [chunk_bot, chunk_top)
+    // PARTS (ensembles of a few waves, where nothing fills the gap a straggling warp leaves): tasks are dealt
+    // dynamically, and a red part starts with its chunks next to the Balmer edge -- inside the line forest, an
+    // order of magnitude more work than a far chunk -- so the CTA's tail is made of light tasks
+    for (int t = SPLIT ? warp * csize + crank : warp;; t += (kThreads / 32) * csize) {
+        if (PARTS) {
+            if (lane == 0) t = atomicAdd(&c.task_next, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+        }
+        if (t >= chunk_top - chunk_bot) break;
+        const int chunk = PARTS && is_red ? chunk_bot + t : chunk_top - 1 - t;
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
         // PAIR (FULL kernel): lane l holds the adjacent pixels 2l, 2l+1 of the chunk, fetched with 16-byte
         // loads; otherwise pixels l and l + 32
@@ -778,7 +912,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         // warp-uniform: does this task hold any Balmer-continuum / pseudo-continuum pixel?  (a non-finite
         // scale keeps the reference's 0 * scale = NaN on every pixel, BC:445-446)
         const bool task_bc = do_bc && (chunk * kChunk <= bc_istar || !bc_finite);
-        const bool task_bpc = do_bpc && chunk * kChunk + kChunk - 1 > bpc_istar;
+        const bool task_bpc = do_bpc && is_red && chunk * kChunk + kChunk - 1 > bpc_istar;
         if (task_bpc) {
             if (lorentz) {
                 // The line sum is a short list of segments, each either a run of line groups summed
@@ -904,8 +1038,35 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         }
     }
 
+#ifdef SPAMM_TRACE
+    if (lane == 0 && g_trace != nullptr) {            // last warp to leave the task loop
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        atomicMax(&g_trace[(size_t)blockIdx.x * 8 + 4], t);
+        if (warp == 0) g_trace[(size_t)blockIdx.x * 8 + 5] = t;
+    }
+#endif
     // ---- per-walker reduction in fixed chunk order + likelihood (Model.py:440-445) ----------------
-    if (MODE == 0) {
+    if (MODE == 0 && PARTS) {
+        __syncthreads();
+        double* gchi = pw.chi + (size_t)wloc * n_chunks;
+        for (int k = chunk_bot + tid; k < chunk_top; k += kThreads) gchi[k] = sChi[k];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) c.prior_ok = (int)atomicAdd(pw.cnt + wloc, 1u);     // (slot reused: 1 = the other part is done)
+        __syncthreads();
+        if (c.prior_ok == 1 && warp == 0) {
+            __threadfence();
+            double s = 0.0;
+            for (int k = lane; k < n_chunks; k += 32) s += __ldcg(gchi + k);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                pw.cnt[wloc] = 0u;
+                double ln_l = -0.5 * (s + pl.sum_ln);
+                store_result(out, w, nan_to_num(ln_l) + 0.0, po);
+            }
+        }
+    } else if (MODE == 0) {
         __syncthreads();
         if (SPLIT) cooperative_groups::this_cluster().sync();          // every CTA's partials are in place
         if (warp == 0 && crank == 0) {

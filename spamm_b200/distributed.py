@@ -5,8 +5,11 @@ pickled (Model, params) tasks: multiprocessing or MPIPool, spamm/Model.py:267-28
 Here every rank holds the full replicated sampler state and an identical
 counter-based RNG, so proposals are generated redundantly and *no parameters
 travel*; each rank evaluates its contiguous slice of the active half-ensemble
-and the only exchange is one all-gather of per-walker ln-probabilities per
-stretch half-step (NCCL over NVLink on GPUs; gloo in the CPU tests).
+and the only exchange is the per-walker ln-probabilities of each stretch half-step.
+On GPUs the walker kernel itself stores them into every rank's exchange region over
+NVLink and raises a flag (`Exchange`, `ExchangeLnPost`; include/spamm_b200.h
+"multi-GPU"); `ShardedLnPost` is the collective form of the same contract
+(all-gather: NCCL, or gloo in the CPU tests).
 """
 import os
 
@@ -80,50 +83,71 @@ class ShardedLnPost(object):
         return torch.cat(parts)
 
 
-class P2PLnPost(object):
-    """ShardedLnPost with the exchange fused into the compute kernel.
+class Exchange(object):
+    """One rank's end of the library's device-side result exchange (`SpammExchange`, include/spamm_b200.h).
 
-    Every rank owns a symmetric (peer-mapped) result buffer; the fused walker kernel stores each
-    ln-posterior directly into all peers' buffers over NVLink (`spamm_lnpost_batch_p2p`), so the
-    only thing left after the kernel is a cross-rank barrier on the symmetric-memory signal pads --
-    no all-gather copy.  Two buffers alternate so a fast rank's next half-step never overwrites
-    values a slower rank is still reading (each step ends in a barrier, so ranks are never more
-    than one step apart)."""
+    The library allocates the region (flag block + two result buffers), this wrapper all-gathers the
+    64-byte CUDA IPC handles over torch.distributed and lets the library map every peer's region; from
+    then on the data path has no collective and no host barrier: the walker kernel stores each
+    ln-posterior into every rank's region over NVLink and raises a flag, consumers wait on the device.
+    All ranks must make the same sequence of sharded calls."""
 
-    def __init__(self, plan, max_n, group=None):
-        import torch.distributed._symmetric_memory as symm
-        self.plan = plan
+    def __init__(self, max_walkers, group=None):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
         self.rank, self.world = world_info()
-        self.group = group if group is not None else dist.group.WORLD
-        self.max_n = int(max_n)
-        self.bufs, self.hdls = [], []
-        for _ in range(2):
-            t = symm.empty(self.max_n, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
-            t.fill_(float("nan"))
-            h = symm.rendezvous(t, self.group)
-            self.bufs.append(t)
-            self.hdls.append(h)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
-        self.step = 0
+        self.group = group
+        self.max_walkers = int(max_walkers)
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.spamm_exchange_create(self.world, self.rank, self.max_walkers, ctypes.byref(h),
+                                                  ctypes.cast(handle, ctypes.c_void_p)))
+        self._h = h
+        if self.world > 1:
+            mine = torch.tensor(list(handle), dtype=torch.uint8)
+            if dist.get_backend(group) == "nccl":
+                mine = mine.cuda()
+            every = torch.empty(self.world * _lib.IPC_HANDLE_BYTES, dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            blob = every.cpu().numpy().tobytes()
+            _lib.check(self.lib.spamm_exchange_connect(self._h, ctypes.c_char_p(blob)))
+            torch.cuda.synchronize()
+            dist.barrier(group=group)            # every region is mapped everywhere before anyone stores
+
+    @property
+    def epoch(self):
+        return int(self.lib.spamm_exchange_epoch(self._h))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            if self.world > 1 and dist.is_initialized():
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)   # no peer still stores into a region that is about to go
+            self.lib.spamm_exchange_destroy(h)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self.lib.spamm_exchange_destroy(h)
+            except Exception:
+                pass
+
+
+class ExchangeLnPost(object):
+    """ShardedLnPost with the exchange fused into the compute kernel (`spamm_lnpost_batch_sharded`):
+    [n, D] replicated parameters -> the full [n] vector on every rank."""
+
+    def __init__(self, plan, max_n, group=None, exchange=None):
+        self.plan = plan
+        self.exchange = exchange if exchange is not None else Exchange(max_n, group=group)
+        self.rank, self.world = self.exchange.rank, self.exchange.world
 
     @staticmethod
     def available():
-        try:
-            import torch.distributed._symmetric_memory  # noqa: F401
-            return torch.cuda.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
-        except Exception:
-            return False
+        return torch.cuda.is_available() and (not dist.is_initialized() or dist.get_backend() == "nccl")
 
-    def __call__(self, params):
-        n = params.shape[0]
-        if n > self.max_n:
-            raise ValueError("P2PLnPost buffer holds %d walkers, got %d" % (self.max_n, n))
-        k = self.step & 1
-        self.step += 1
-        buf, hdl = self.bufs[k], self.hdls[k]
-        lo, hi, _ = shard_bounds(n, self.world, self.rank)
-        if hi > lo:
-            self.plan.lnposterior_p2p(params[lo:hi].contiguous(), hdl.buffer_ptrs_dev, self.world, lo)
-        hdl.barrier(channel=0)
-        return buf[:n]
+    def __call__(self, params, out=None):
+        return self.plan.lnposterior_sharded(params, self.exchange, out=out)

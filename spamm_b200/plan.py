@@ -110,7 +110,7 @@ class ModelPlan(object):
         return bool(self.lib.spamm_plan_specialised(self._h))
 
     def set_walker_split(self, mode):
-        """0: one CTA per walker always; 1: automatic cluster split for small ensembles; 2/4/8: forced."""
+        """0: one CTA per walker always; 1: automatic; 2/4/8: forced cluster size; 3: forced two-part split."""
         _lib.check(self.lib.spamm_plan_set_walker_split(self._h, int(mode)))
 
     def status(self):
@@ -126,6 +126,37 @@ class ModelPlan(object):
             out = torch.empty(W, dtype=torch.float64, device=params.device)
         _lib.check(self.lib.spamm_lnpost_batch(self._h, ctypes.c_void_p(params.data_ptr()), W,
                                                ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def check(self):
+        """Synchronise the current stream and raise SpammError if any walker so far needed a table entry
+        the plan does not hold (its ln-posterior would be wrong, not -inf); clears the condition."""
+        _lib.check(self.lib.spamm_plan_check(self._h, self._stream()))
+
+    def lnposterior_sharded(self, params, exchange, out=None):
+        """Multi-GPU form of `lnposterior`: params is the full replicated [n, D] tensor; this rank
+        evaluates its slice and the kernel stores the results into every rank's exchange region.
+        Returns the gathered [n] vector (a copy in `out`), complete in stream order."""
+        torch = _torch()
+        self._check_params(params)
+        n = params.shape[0]
+        if out is None:
+            out = torch.empty(n, dtype=torch.float64, device=params.device)
+        _lib.check(self.lib.spamm_lnpost_batch_sharded(self._h, exchange._h, ctypes.c_void_p(params.data_ptr()), n,
+                                                       ctypes.c_void_p(out.data_ptr()), None, self._stream()))
+        return out
+
+    def lnposterior_sharded_host(self, params, exchange, out=None):
+        """numpy [n, D] (the same array on every rank) -> numpy [n]: H2D of this rank's rows, kernel +
+        exchange, D2H of the gathered vector, inside the library."""
+        p = np.ascontiguousarray(np.atleast_2d(params), dtype=np.float64)
+        if p.shape[1] != self.n_dim:
+            raise ValueError("expected %d parameters per walker, got %d" % (self.n_dim, p.shape[1]))
+        if out is None:
+            out = np.empty(p.shape[0], dtype=np.float64)
+        assert out.dtype == np.float64 and out.shape == (p.shape[0],) and out.flags.c_contiguous
+        _lib.check(self.lib.spamm_lnpost_batch_sharded_host(self._h, exchange._h, p.ctypes.data_as(ctypes.c_void_p),
+                                                            p.shape[0], out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
     def lnposterior_p2p(self, params, peer_bufs_dev, n_peers, elem_offset):

@@ -85,7 +85,8 @@ def spamm(complist, inspectrum, par_file=None, n_walkers=30, n_iterations=500, o
     print("Mean acceptance fraction: {0:.3f}".format(np.mean(model.sampler.acceptance_fraction)))
 
     p_data = {"model": model, "comp_params": comp_params}
-    if save:
+    from .distributed import world_info
+    if save and world_info()[0] == 0:          # under torchrun every rank holds the same chain: rank 0 writes it
         now = datetime.datetime.now().strftime("%Y%m%d_%M%S")
         if picklefile is None:
             picklefile = "model_{0}.pickle.gz".format(now)

@@ -83,20 +83,31 @@ class EnsembleSampler(object):
         self._walkers = None
         self._lnp = None
         self._nacc = None
-        # multi-GPU: each rank evaluates its slice; results reach every rank either by P2P stores
-        # from the compute kernel (symmetric memory + barrier) or, as a fallback, an NCCL all-gather
+        # multi-GPU: each rank evaluates its slice of every half-step.  Default: the library's device-side
+        # exchange (walker kernel stores into every rank's region over NVLink + flags; the whole loop runs
+        # inside spamm_stretch_run_sharded).  SPAMM_EXCHANGE=nccl: all-gather per half-step from Python.
         import os
-        from .distributed import ShardedLnPost, P2PLnPost, world_info
+        from .distributed import ShardedLnPost, ExchangeLnPost, Exchange, world_info
         self.exchange = "single"
-        if world_info()[1] > 1:
-            if os.environ.get("SPAMM_EXCHANGE", "p2p") == "p2p" and P2PLnPost.available():
-                self._evaluate = P2PLnPost(self.plan, max_n=nwalkers)
+        self._xch = None
+        self.rank, self.world = world_info()
+        if self.world > 1:
+            import torch.distributed as dist
+            # every rank proposes the whole half-ensemble from the same counter-based RNG: the seed (and, in
+            # run_mcmc, the start state) must be rank 0's, whatever each rank's own numpy RNG drew
+            box = [self.seed]
+            dist.broadcast_object_list(box, src=0)
+            self.seed = int(box[0])
+            if os.environ.get("SPAMM_EXCHANGE", "p2p") == "p2p" and ExchangeLnPost.available():
+                self._xch = Exchange(nwalkers)
+                self._evaluate = ExchangeLnPost(self.plan, nwalkers, exchange=self._xch)
                 self.exchange = "p2p"
             else:
                 self._evaluate = ShardedLnPost(self.plan.lnposterior)
                 self.exchange = "nccl"
         else:
             self._evaluate = ShardedLnPost(self.plan.lnposterior)
+        self._run = 0                    # bumped by reset(): a new run draws a fresh random stream
 
     # -- emcee-style accessors --------------------------------------------------
     @property
@@ -137,7 +148,20 @@ class EnsembleSampler(object):
     def __setstate__(self, d):
         self.__dict__.update(d)
 
+    def _rng_seed(self):
+        # the Philox counter is keyed by (seed, iteration, half, walker); reset() restarts the iteration
+        # count, so the run index is folded into the key -- a production run after a burn-in must not
+        # replay the burn-in's random numbers
+        return (self.seed + 0x9E3779B97F4A7C15 * self._run) & 0xFFFFFFFFFFFFFFFF
+
+    def close(self):
+        """Release the multi-GPU exchange region (collective: every rank must call it)."""
+        if self._xch is not None:
+            self._xch.close()
+            self._xch = None
+
     def reset(self):
+        self._run += 1
         self.iterations = 0
         self._chain = self._lnprob = None
         if self._nacc is not None:
@@ -153,14 +177,14 @@ class EnsembleSampler(object):
         vp = ctypes.c_void_p
         st = self._stream()
         _lib.check(self.lib.spamm_stretch_propose(vp(self._walkers.data_ptr()), self.k, self.dim, half,
-                                                  self.a, self.seed, it, vp(self._q.data_ptr()),
+                                                  self.a, self._rng_seed(), it, vp(self._q.data_ptr()),
                                                   vp(self._z.data_ptr()), st))
         lnp_q = self._evaluate(self._q)
         if not lnp_q.is_contiguous():
             lnp_q = lnp_q.contiguous()
         _lib.check(self.lib.spamm_stretch_accept(vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()),
                                                  self.k, self.dim, half, vp(self._q.data_ptr()),
-                                                 vp(self._z.data_ptr()), vp(lnp_q.data_ptr()), self.seed,
+                                                 vp(self._z.data_ptr()), vp(lnp_q.data_ptr()), self._rng_seed(),
                                                  it, vp(self._nacc.data_ptr()), st))
 
     def run_mcmc(self, pos0, N, lnprob0=None):
@@ -175,6 +199,9 @@ class EnsembleSampler(object):
             raise ValueError("At least one parameter value was NaN.")
         dev = torch.device("cuda", torch.cuda.current_device())
         self._walkers = torch.from_numpy(p0).to(dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self._walkers, src=0)         # the replicated state is rank 0's
         self._q = torch.empty((self.k // 2, self.dim), dtype=torch.float64, device=dev)
         self._z = torch.empty(self.k // 2, dtype=torch.float64, device=dev)
         if self._nacc is None:
@@ -183,6 +210,8 @@ class EnsembleSampler(object):
             self._lnp = self._evaluate(self._walkers).clone()
         else:
             self._lnp = torch.from_numpy(np.array(lnprob0, dtype=np.float64)).to(dev)
+            if self.world > 1:
+                dist.broadcast(self._lnp, src=0)
         if bool(torch.isnan(self._lnp).any()):
             raise ValueError("The initial lnprob was NaN.")
         start = self.iterations
@@ -204,7 +233,21 @@ class EnsembleSampler(object):
                 n = min(256, total - it)
                 _lib.check(self.lib.spamm_stretch_run(
                     self.plan._h, vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()), self.k, self.a,
-                    self.seed, it, n, vp(self._q.data_ptr()), vp(self._z.data_ptr()), vp(lnp_q.data_ptr()),
+                    self._rng_seed(), it, n, vp(self._q.data_ptr()), vp(self._z.data_ptr()), vp(lnp_q.data_ptr()),
+                    vp(self._nacc.data_ptr()),
+                    vp(self._chain.data_ptr()) if self.store_chain else None,
+                    vp(self._lnprob.data_ptr()) if self.store_chain else None, total, self._stream()))
+                it += n
+                self.iterations += n
+        elif self.exchange == "p2p" and self.native_loop:
+            # several devices: the same loop inside the library, every half-step's proposals sharded over
+            # the ranks and exchanged by the walker kernel itself (spamm_stretch_run_sharded)
+            it = start
+            while it < total:
+                n = min(256, total - it)
+                _lib.check(self.lib.spamm_stretch_run_sharded(
+                    self.plan._h, self._xch._h, vp(self._walkers.data_ptr()), vp(self._lnp.data_ptr()), self.k,
+                    self.a, self._rng_seed(), it, n, vp(self._q.data_ptr()), vp(self._z.data_ptr()),
                     vp(self._nacc.data_ptr()),
                     vp(self._chain.data_ptr()) if self.store_chain else None,
                     vp(self._lnprob.data_ptr()) if self.store_chain else None, total, self._stream()))
@@ -221,6 +264,7 @@ class EnsembleSampler(object):
                                                            self._stream()))
                 self.iterations += 1
         torch.cuda.synchronize()
+        self.plan.check()                # a walker outside the plan's tables is an error, not a number
         pos = self._walkers.cpu().numpy()
         lnp = self._lnp.cpu().numpy()
         self._last_run_mcmc_result = (pos, lnp, None)

@@ -444,7 +444,7 @@ def test_walker_split_over_cluster_is_bit_identical():
             ok = np.isfinite(c.lnpost[:30])
             ok[3] = False
             assert rel_err(base[ok], c.lnpost[:30][ok]).max() < LNPOST_RTOL
-        for split in (2, 4, 8, 1):
+        for split in (2, 3, 4, 8, 1):
             m.plan.set_walker_split(split)
             got = m.lnposterior_batch(params)
             assert np.array_equal(got, base), (name, split, np.abs(got - base).max())
@@ -469,7 +469,7 @@ def test_full_model_specialisation_equals_generic_kernel(monkeypatch):
     assert rel_err(got, ref).max() < 1e-13
     assert np.array_equal(np.isneginf(got), np.isneginf(ref))
     assert rel_err(got, c.lnpost).max() < LNPOST_RTOL
-    for split in (2, 8):
+    for split in (2, 3, 8):
         m_full.plan.set_walker_split(split)
         assert np.array_equal(m_full.lnposterior_batch(c.params), got)
 
@@ -567,7 +567,7 @@ def test_specialised_kernel_on_awkward_grids(monkeypatch):
         gen = gplan.lnposterior_host(params)
         monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
         assert rel_err(got, gen).max() < 1e-12, (len(wl), wl[0])
-        for split in (0, 2, 4, 8):
+        for split in (0, 2, 3, 4, 8):
             full.set_walker_split(split)
             assert np.array_equal(full.lnposterior_host(params), got), (len(wl), split)
         assert full.status() == 0
@@ -590,7 +590,7 @@ def test_specialised_instantiations_of_the_baseline_configs(name, monkeypatch):
     ref = g.lnposterior_batch(c.params)
     monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
     assert rel_err(got, ref).max() < 1e-13
-    for split in (2, 4, 8):
+    for split in (2, 3, 4, 8):
         m.plan.set_walker_split(split)
         assert np.array_equal(m.lnposterior_batch(c.params), got)
 
@@ -774,7 +774,7 @@ def test_specialised_three_component_models(comps, monkeypatch):
     ref = g.lnposterior_batch(params)
     monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
     assert rel_err(got, ref).max() < 1e-13
-    for split in (2, 4, 8):
+    for split in (2, 3, 4, 8):
         m.plan.set_walker_split(split)
         assert np.array_equal(m.lnposterior_batch(params), got)
 
@@ -810,7 +810,7 @@ def test_specialised_balmer_with_one_part_off(comps, bc, bpc, monkeypatch):
     ref = g.lnposterior_batch(params)
     monkeypatch.delenv("SPAMM_NO_FULL_KERNEL")
     assert rel_err(got, ref).max() < 1e-13
-    for split in (2, 4, 8):
+    for split in (2, 3, 4, 8):
         m.plan.set_walker_split(split)
         assert np.array_equal(m.lnposterior_batch(params), got)
     assert m.plan.status() == 0
