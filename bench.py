@@ -1,15 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- ln-posterior evaluations per second of the full NC+Fe+HG+BC model.
+"""bench.py -- ln-posterior evaluations per second of the full NC+Fe+HG+BC model (BASELINE config 5).
 
     python bench.py --gpus N --steps K --warmup W            (our CUDA path)
-    python bench.py --impl reference --gpus N --steps K ...   (the CPU restatement of
-                                                               the reference, all host cores)
+    python bench.py --impl reference --gpus N --steps K ...   (the reference's own ln_posterior on the
+                                                               host cores: oracle/_ref under oracle/refshim)
 
-A "step" is one batched ln-posterior call over the rank's walker ensemble
-(BASELINE.json config 5: 8192 walkers x 8192 pixels, D = 20, FP64), parameters
-already resident in HBM, followed -- when N > 1 -- by the all-gather of the
-per-walker ln-probabilities (the only exchange of the stretch move).  One JSON
-line is printed by rank 0.
+Workload: ONE ensemble of 8192 walkers x 8192 pixels, D = 20, FP64.  A "step" is the ln-posterior work of
+one stretch-move iteration of that ensemble: two batched calls of one half-ensemble (4096 walkers) each --
+the stretch move updates the halves alternately, so a half is the largest batch a sampler can hand over --
+with the parameters already resident in HBM.  On N > 1 GPUs every half is sharded N ways (strong scaling:
+the ensemble does not grow) and each call ends with the per-walker results on EVERY rank: the walker kernel
+stores them into all ranks' exchange regions over NVLink and raises a flag, and a wait for all flags is
+queued behind it (include/spamm_b200.h, "multi-GPU").  `value` = 8192 * K / time, timed with CUDA events,
+max over ranks.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -30,6 +33,7 @@ UNIT = "evals/s"
 N_PIX = 8192
 N_WALKERS = 8192
 COMPONENTS = ("PL", "FE", "HOST", "BC")
+WORKLOAD = "config5: one ensemble of 8192 walkers x 8192 px, full NC+Fe+HG+BC, D=20, walkers from the priors (seed 42)"
 
 
 # ---------------------------------------------------------------------------
@@ -59,9 +63,9 @@ FE_RANGES = ((1074.987, 3089.96), (3090.0, 3534.0), (3535.0, 7535.0))
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler(object):
-    """SM clock, power and throttle reasons polled through NVML every 5 ms while the timed
-    region runs (the region lasts tens of milliseconds, too short for `nvidia-smi -lms`);
-    falls back to one nvidia-smi query if NVML is unavailable."""
+    """SM clock, power and throttle reasons polled through NVML every 5 ms while a timed region runs
+    (`nvidia-smi -lms` cannot sample a region of tens of milliseconds); falls back to one nvidia-smi
+    query if NVML is unavailable."""
 
     def __init__(self, index=0):
         self.index = index
@@ -80,6 +84,7 @@ class ClockSampler(object):
             self.thread.start()
         except Exception:
             self.nv = None
+        return self
 
     def _poll(self):
         nv = self.nv
@@ -120,30 +125,54 @@ class ClockSampler(object):
                 if rs & bit:
                     reasons.add(n)
         return {"sm_mhz": float(np.median([s[1] for s in inside])), "sm_max_mhz": float(smax),
+                "sm_mhz_min": float(np.min([s[1] for s in inside])),
+                "power_w_median": float(np.median([s[2] for s in inside])),
                 "power_w_max": float(np.max([s[2] for s in inside])), "samples": len(inside),
                 "reasons": sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------
-# CPU baseline: the numpy restatement of the reference, one process per core
+# CPU legs.  kind "reference": the UNMODIFIED reference (spamm.Model.ln_posterior, Model.py:42-79) from
+# oracle/_ref, one Model per worker process, multiprocessing.Pool(cores).map -- exactly what emcee's
+# threads=n does with it (Model.py:283-286).  kind "port": the numpy restatement (oracle/spamm_numpy.py),
+# a faster CPU program, reported beside it.
 # ---------------------------------------------------------------------------
-_ORACLE = None
+_CPU_MODEL = None
+_CPU_KIND = None
 
 
-def _oracle_init(wl, flux, err):
-    global _ORACLE
+def _cpu_init(kind, wl, flux, err):
+    global _CPU_MODEL, _CPU_KIND
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle.spamm_numpy import OracleModel
-    _ORACLE = OracleModel(wl, flux, err, comps=list(COMPONENTS))
-    _ORACLE.bounds()
+    import warnings
+    warnings.filterwarnings("ignore")
+    _CPU_KIND = kind
+    if kind == "reference":
+        from oracle import ref_runner
+        _CPU_MODEL = ref_runner.build_model(wl, flux, err, COMPONENTS)
+    else:
+        from oracle.spamm_numpy import OracleModel
+        _CPU_MODEL = OracleModel(wl, flux, err, comps=list(COMPONENTS))
+        _CPU_MODEL.bounds()
 
 
-def _oracle_eval(p):
-    return _ORACLE.ln_posterior(p)
+def _cpu_eval(p):
+    if _CPU_KIND == "reference":
+        from oracle import ref_runner
+        return ref_runner.ln_posterior(_CPU_MODEL, p)
+    return _CPU_MODEL.ln_posterior(p)
+
+
+def reference_available():
+    try:
+        from oracle import ref_runner
+        return ref_runner.available()
+    except Exception:
+        return False
 
 
 def oracle_workload(n_walkers, seed=42):
-    """Same workload built without touching the GPU path (reference arm)."""
+    """The config-5 workload built without touching the GPU path (reference arm)."""
     from oracle.spamm_numpy import OracleModel
     wl = 1000.0 + np.arange(N_PIX) * (9000.0 / N_PIX)
     truth = {"PL": [5e-15, 2.3], "FE": [1.07988504e-14, 6.91877436e-15, 5e-15, 5450.],
@@ -159,21 +188,25 @@ def oracle_workload(n_walkers, seed=42):
     return wl, flux, err, params
 
 
-def cpu_pool_throughput(wl, flux, err, params, cores, repeats=1):
-    """evals/s of multiprocessing.Pool(cores).map(ln_posterior, walkers) -- what
-    emcee's threads=n does with the reference (spamm/Model.py:283-286)."""
+def cpu_pool_throughput(kind, wl, flux, err, params, cores):
+    """evals/s of multiprocessing.Pool(cores).map(ln_posterior, walkers)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores, initializer=_oracle_init, initargs=(wl, flux, err)) as pool:
-        pool.map(_oracle_eval, list(params[:cores]))       # warm the workers
-        best = 0.0
-        vals = None
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            vals = pool.map(_oracle_eval, list(params), chunksize=max(1, len(params) // (4 * cores)))
-            dt = time.perf_counter() - t0
-            best = max(best, len(params) / dt)
-    return best, np.array(vals)
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(kind, wl, flux, err)) as pool:
+        pool.map(_cpu_eval, list(params[:cores]))       # warm the workers
+        t0 = time.perf_counter()
+        vals = pool.map(_cpu_eval, list(params), chunksize=max(1, len(params) // (4 * cores)))
+        dt = time.perf_counter() - t0
+    return len(params) / dt, np.array(vals)
+
+
+def cpu_one_core(kind, wl, flux, err, params):
+    _cpu_init(kind, wl, flux, err)
+    _cpu_eval(params[0])
+    t0 = time.perf_counter()
+    for p1 in params:
+        _cpu_eval(p1)
+    return len(params) / (time.perf_counter() - t0)
 
 
 def run_reference(args):
@@ -181,34 +214,35 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    kind = "reference" if reference_available() else "port"
     per_step = max(8 * cores, 64)
-    n = per_step * (args.steps + args.warmup)
-    wl, flux, err, params = oracle_workload(min(n, 4096))
+    wl, flux, err, params = oracle_workload(min(per_step * (args.steps + args.warmup), 4096))
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(cores, initializer=_oracle_init, initargs=(wl, flux, err)) as pool:
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(kind, wl, flux, err)) as pool:
         for s in range(args.warmup + args.steps):
             chunk = params[(s * per_step) % len(params):][:per_step]
             if len(chunk) < per_step:
                 chunk = params[:per_step]
             t0 = time.perf_counter()
-            pool.map(_oracle_eval, list(chunk), chunksize=max(1, per_step // (4 * cores)))
+            pool.map(_cpu_eval, list(chunk), chunksize=max(1, per_step // (4 * cores)))
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
     total = float(np.sum(times))
     value = per_step * args.steps / total
-    sample = "%d walkers per step x %d steps of the config-5 ensemble, numpy port of the reference, " \
-             "multiprocessing.Pool(%d)" % (per_step, args.steps, cores)
+    what = "the reference's own ln_posterior (spamm/Model.py:42-79, unmodified, oracle/_ref under oracle/refshim)" \
+        if kind == "reference" else "numpy port of the reference (oracle/spamm_numpy.py; oracle/_ref absent)"
+    sample = "%d walkers per step x %d steps of the config-5 ensemble, %s, multiprocessing.Pool(%d).map" \
+             % (per_step, args.steps, what, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "config5: full NC+Fe+HG+BC, 8192 px, D=20, walkers from priors (seed 42)",
-                   "walkers_per_step": per_step, "n_pix": N_PIX},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "walkers_total": N_WALKERS, "walkers_per_step": per_step, "n_pix": N_PIX},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,11 +253,17 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
+def _events(n):
+    import torch
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
 def run_ours(args):
+    import ctypes
     import torch
     import torch.distributed as dist
     from spamm_b200 import _lib
-    from spamm_b200.distributed import init_from_env
+    from spamm_b200.distributed import init_from_env, Exchange
     from spamm_b200.synth import full_model_workload
 
     rank, world, local_rank = init_from_env("nccl")
@@ -231,57 +271,43 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
 
-    n_local = args.walkers
-    if args.scaling == "strong":
-        n_local = (args.walkers + world - 1) // world
-    model, params_all = full_model_workload(N_PIX, args.walkers if args.scaling == "strong" else args.walkers,
-                                            seed=42 + (rank if args.scaling == "weak" else 0))
-    if args.scaling == "strong":
-        params_host = np.ascontiguousarray(params_all[rank * n_local:(rank + 1) * n_local])
-        n_local = len(params_host)
-    else:
-        params_host = params_all
+    W = args.walkers
+    Wh = W // 2
+    model, params_host = full_model_workload(N_PIX, W, seed=42)          # the same ensemble on every rank
     plan = model.plan
     params = torch.from_numpy(params_host).to(dev)
-    lnp = torch.empty(n_local, dtype=torch.float64, device=dev)
-    gathered = torch.empty(n_local * world, dtype=torch.float64, device=dev) if world > 1 else None
+    halves = [params[:Wh].contiguous(), params[Wh:].contiguous()]
+    halves_host = [np.ascontiguousarray(params_host[:Wh]), np.ascontiguousarray(params_host[Wh:])]
+    lnp = [torch.empty(Wh, dtype=torch.float64, device=dev) for _ in range(2)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    exchange = "none"
-    p2p = None
-    if world > 1:
-        from spamm_b200.distributed import P2PLnPost
-        exchange = "nccl all_gather"
-        if args.exchange == "p2p" and P2PLnPost.available():
-            try:
-                p2p = P2PLnPost(plan, max_n=n_local * world)
-                exchange = "P2P stores from the compute kernel into every peer's symmetric buffer + barrier"
-            except Exception as exc:                                  # symmetric memory unavailable
-                p2p = None
-                exchange = "nccl all_gather (p2p unavailable: %s)" % type(exc).__name__
-    p2p_step = [0]
+    ex = Exchange(W) if world > 1 else None
+    per_gpu = -(-Wh // world)
 
     def step():
-        if p2p is not None:
-            k = p2p_step[0] & 1
-            p2p_step[0] += 1
-            plan.lnposterior_p2p(params, p2p.hdls[k].buffer_ptrs_dev, world, rank * n_local)
-            p2p.hdls[k].barrier(channel=0)
-            return
-        plan.lnposterior(params, out=lnp)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, lnp)
+        for h in range(2):
+            if ex is None:
+                plan.lnposterior(halves[h], out=lnp[h])
+            else:
+                plan.lnposterior_sharded(halves[h], ex, copy=False)     # results + flag wait, in the region
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # FP64 peak for the roofline denominator (MEASURED_PEAKS.json has no FP64 entry)
-    import ctypes
     peak = ctypes.c_double(0.0)
     _lib.check(lib.spamm_fp64_peak_probe(20000, 5, ctypes.byref(peak)))
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     barrier()
 
@@ -290,8 +316,7 @@ def run_ours(args):
         clocks.start()
         time.sleep(0.05)
     launches0 = plan.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
+    evs = _events(args.steps)
     barrier()
     t_wall0 = time.time()
     for e0, e1 in evs:
@@ -303,194 +328,297 @@ def run_ours(args):
     t_wall1 = time.time()
     launches = plan.launch_count - launches0
     ms = np.array([e0.elapsed_time(e1) for e0, e1 in evs])
-    total_ms = float(ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(float(ms.sum()))
     clk = clocks.stop(t_wall0, t_wall1) if rank == 0 else None
+    value = W * args.steps / (total_ms * 1e-3)
 
-    # end to end through the public API with host buffers (H2D + kernel + D2H every step)
+    # ---- correctness of what was timed: every rank must hold the WHOLE vector of each half, equal bit for
+    # bit to the unsharded evaluation of the same parameters on this rank
+    local_full = [plan.lnposterior(halves[h]).cpu().numpy() for h in range(2)]
+    verified = True
+    if ex is not None:
+        for h in range(2):
+            got = plan.lnposterior_sharded(halves[h], ex).cpu().numpy()
+            verified = verified and np.array_equal(got, local_full[h])
+        flag = torch.tensor([0.0 if verified else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        assert float(flag.item()) == 0.0, "the exchanged ln-posterior vector differs from the unsharded one on some rank"
+    plan.check()
+
+    # ---- end to end through the public API with HOST buffers: per half, H2D of (this rank's share of) the
+    # parameters from pinned memory, kernel (+ exchange), D2H of the whole half's results, synchronise
     e2e_steps = max(3, min(args.steps, 10))
-    pin_in = torch.empty(params_host.shape, dtype=torch.float64, pin_memory=True)
-    pin_out = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
-    pin_in.numpy()[...] = params_host                 # the step's inputs live in pinned host memory
-    h_in, h_out = pin_in.numpy(), pin_out.numpy()
-    model.lnposterior_batch(h_in, out=h_out)
+    pin_in = [torch.empty(h.shape, dtype=torch.float64, pin_memory=True) for h in halves_host]
+    pin_out = [torch.empty(Wh, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    for t, h in zip(pin_in, halves_host):
+        t.numpy()[...] = h
+    h_in, h_out = [t.numpy() for t in pin_in], [t.numpy() for t in pin_out]
+    call = model.lnposterior_batch_sharded if world > 1 else model.lnposterior_batch
+    for h in range(2):
+        call(h_in[h], out=h_out[h])
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        res = model.lnposterior_batch(h_in, out=h_out)      # H2D + kernel + D2H + sync, every step
-    t_e2e = time.perf_counter() - t0
-    res = np.array(res)
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-    e2e_value = n_local * world * e2e_steps / t_e2e
-    if p2p is not None:
-        # every rank's buffer holds the whole gathered vector; this rank's slice must equal
-        # what the plain local call returns
-        got = p2p.bufs[(p2p_step[0] - 1) & 1][rank * n_local:(rank + 1) * n_local].cpu().numpy()
-        plan.lnposterior(params, out=lnp)
-        assert np.array_equal(got, lnp.cpu().numpy()), "P2P-exchanged results differ from the local call"
-    assert np.array_equal(res, lnp.cpu().numpy()), "host-buffer and device-buffer paths disagree"
+        for h in range(2):
+            call(h_in[h], out=h_out[h])
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = W * e2e_steps / t_e2e
+    for h in range(2):
+        assert np.array_equal(h_out[h], local_full[h]), "host-buffer and device-buffer paths disagree"
+    lo_r = min(rank * per_gpu, Wh)
+    hi_r = min(lo_r + per_gpu, Wh)
+    h2d = 2 * (hi_r - lo_r) * plan.n_dim * 8
+    d2h = 2 * Wh * 8
 
-    value = n_local * world * args.steps / (total_ms * 1e-3)
+    secondary = {}
+    # ---- the same ensemble in ONE call of 8192 walkers (round 1's step), device-timed, one GPU
+    if world == 1:
+        lnp_all = torch.empty(W, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            plan.lnposterior(params, out=lnp_all)
+        ev1 = _events(5)
+        for e0, e1 in ev1:
+            flush.zero_()
+            e0.record()
+            plan.lnposterior(params, out=lnp_all)
+            e1.record()
+        torch.cuda.synchronize()
+        one_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev1]))
+        secondary["single_call_8192"] = {"ms": one_ms, "evals_per_s": W / (one_ms * 1e-3)}
 
-    # the same ensemble with every Balmer line summed directly (bc_exact_line_sum): this kernel
-    # executes the algorithmic flops of SURVEY.md 8(d), so its FP64 fraction is the comparable one
-    exact_ms = None
-    if rank == 0 and not args.no_exact:
+    # ---- the kernel that executes every algorithmic flop (bc_exact_line_sum): its FP64 fraction is the one
+    # comparable with the SURVEY 8(d) count
+    exact = None
+    if rank == 0 and world == 1 and not args.no_exact:
         from spamm_b200.synth import build_model
         ds = model.data_spectrum
         m2 = build_model(list(COMPONENTS), np.asarray(ds.spectral_axis), np.asarray(ds.flux),
-                         np.asarray(ds.flux_error), max_walkers=n_local)
+                         np.asarray(ds.flux_error), max_walkers=Wh)
         m2.components[-1].exact_line_sum = True
-        lnp2 = torch.empty_like(lnp)
-        for _ in range(3):
-            m2.plan.lnposterior(params, out=lnp2)
+        lnp2 = torch.empty(Wh, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            m2.plan.lnposterior(halves[0], out=lnp2)
         torch.cuda.synchronize()
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        ev2 = _events(3)
         for e0, e1 in ev2:
             flush.zero_()
             e0.record()
-            m2.plan.lnposterior(params, out=lnp2)
+            m2.plan.lnposterior(halves[0], out=lnp2)
             e1.record()
         torch.cuda.synchronize()
         exact_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev2]))
-        a, b = lnp.cpu().numpy(), lnp2.cpu().numpy()
-        exact_rel = float(np.max(np.abs(a - b) / np.abs(b)))
+        b = lnp2.cpu().numpy()
+        exact = {"ms_per_half": exact_ms, "evals_per_s": Wh / (exact_ms * 1e-3),
+                 "max_rel_diff_vs_default": float(np.max(np.abs(local_full[0] - b) / np.abs(b)))}
+        del m2
 
-    # secondary figures of SURVEY.md 8(d): one stretch half-step (W/2 walkers per call) and the whole
-    # device sampler (walkers x iterations per second, proposals + ln-posterior + accept + chain record)
-    secondary = None
-    if world == 1 and not args.no_sampler:
+    # ---- the whole device sampler on this ensemble (emcee 2.2.1 stretch move inside the library):
+    # walkers x iterations per second, every half-step sharded over the N GPUs
+    if not args.no_sampler:
         from spamm_b200.sampler import EnsembleSampler
         from spamm_b200.Model import ln_posterior
-        half = params[: n_local // 2].contiguous()
-        lnp_h = torch.empty(len(half), dtype=torch.float64, device=dev)
-        for _ in range(3):
-            plan.lnposterior(half, out=lnp_h)
+        n_it = args.sampler_iterations
+        smp = EnsembleSampler(nwalkers=W, dim=plan.n_dim, lnpostfn=ln_posterior, args=[model], seed=7,
+                              store_chain=True)
+        smp.run_mcmc(params_host, 5)         # burn the start-up transient; one-off allocations
+        pos = smp._walkers.cpu().numpy()
+        cs = ClockSampler(local_rank).start() if rank == 0 else None
+        for _ in range(2):                   # the first pass pays the allocation of the longer chain buffers
+            smp.reset()
+            barrier()
+            tw0 = time.time()
+            t0 = time.perf_counter()
+            smp.run_mcmc(pos, n_it)
+            dt = max_over_ranks(time.perf_counter() - t0)
+            tw1 = time.time()
+        sclk = cs.stop(tw0, tw1) if cs is not None else None
+        chain_sum = float(np.asarray(smp.chain[:, -1, :]).sum())
+        if world > 1:                        # every rank must hold the same chain
+            t = torch.tensor([chain_sum, -chain_sum], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            assert float(t[0].item()) == chain_sum and float(t[1].item()) == -chain_sum, "ranks disagree on the chain"
+        secondary["sampler"] = {"walkers": int(W), "iterations": n_it, "ms_per_iteration": 1e3 * dt / n_it,
+                                "walker_steps_per_s": W * n_it / dt, "exchange": smp.exchange,
+                                "acceptance_fraction": float(smp.acceptance_fraction.mean()), "clocks": sclk,
+                                "what": "emcee 2.2.1 stretch move inside the library (spamm_stretch_run%s): propose, "
+                                        "ln-posterior, accept for both halves, chain record; wall clock, max over ranks"
+                                        % ("_sharded" if world > 1 else "")}
+        smp.close()
+
+    # ---- sustained: >= args.sustained seconds of back-to-back steps with the clock record
+    if world == 1 and args.sustained > 0:
+        n_guess = int(args.sustained / (total_ms / args.steps * 1e-3)) + 1
+        cs = ClockSampler(local_rank).start()
+        time.sleep(0.02)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        evh = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
-        for e0, e1 in evh:
+        tw0 = time.time()
+        e0.record()
+        done = 0
+        while done < n_guess:
+            for _ in range(256):
+                step()
+            done += 256
+            if done % 2048 == 0:                      # keep the launch queue bounded
+                torch.cuda.current_stream().synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        tw1 = time.time()
+        s_ms = e0.elapsed_time(e1)
+        secondary["sustained"] = {"seconds": s_ms * 1e-3, "steps": done, "ms_per_step": s_ms / done,
+                                  "evals_per_s": W * done / (s_ms * 1e-3),
+                                  "vs_burst": (W * done / (s_ms * 1e-3)) / value,
+                                  "l2": "no flush (back-to-back steps; the 13 MB template bank stays in L2)",
+                                  "clocks": cs.stop(tw0, tw1)}
+        plan.check()
+
+    # ---- weak scaling (secondary): 8192 walkers per GPU in one sharded call
+    if world > 1 and not args.no_weak:
+        exw = Exchange(W * world)
+        pw = params.repeat(world, 1).contiguous()
+        for _ in range(3):
+            plan.lnposterior_sharded(pw, exw, copy=False)
+        barrier()
+        evw = _events(5)
+        for e0, e1 in evw:
             flush.zero_()
             e0.record()
-            plan.lnposterior(half, out=lnp_h)
+            plan.lnposterior_sharded(pw, exw, copy=False)
             e1.record()
-        torch.cuda.synchronize()
-        half_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evh]))
-        n_it = 40
-        for _ in range(2):         # the first pass pays the one-off device allocations of the chain buffers
-            smp = EnsembleSampler(nwalkers=n_local, dim=plan.n_dim, lnpostfn=ln_posterior, args=[model], seed=7,
-                                  store_chain=True)
-            smp.run_mcmc(params_host, 5)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            smp.run_mcmc(smp._walkers.cpu().numpy(), n_it)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        secondary = {"half_step": {"walkers": int(len(half)), "ms": half_ms,
-                                   "evals_per_s": len(half) / (half_ms * 1e-3)},
-                     "sampler": {"walkers": int(n_local), "iterations": n_it, "ms_per_iteration": 1e3 * dt / n_it,
-                                 "walker_steps_per_s": n_local * n_it / dt,
-                                 "acceptance_fraction": float(smp.acceptance_fraction.mean()),
-                                 "what": "emcee 2.2.1 stretch move on the device (spamm_stretch_run): propose, "
-                                         "ln-posterior, accept for both halves, chain record; wall clock"}}
+        barrier()
+        w_ms = max_over_ranks(float(np.sum([e0.elapsed_time(e1) for e0, e1 in evw])))
+        secondary["weak"] = {"walkers_per_gpu": W, "walkers_total": W * world, "ms_per_call": w_ms / 5,
+                             "evals_per_s": W * world * 5 / (w_ms * 1e-3)}
+        exw.close()
 
-    line = None
     if rank == 0:
         wl = np.asarray(model.data_spectrum.spectral_axis)
         flops = algorithmic_flops(wl, FE_RANGES)
-        achieved = flops * (n_local * args.steps / (total_ms * 1e-3)) / 1e12    # this GPU's share
-        traffic, pipe_busy = None, None
+        prof = {}
         tpath = os.path.join(ROOT, "profiles", "k_walkers_traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            traffic, pipe_busy = tj.get("dram_bytes_per_launch"), tj.get("fp64_pipe_busy_default")
-        roofline = {"bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
-                    "frac": achieved / float(peak.value) if peak.value else None, "traffic": traffic,
-                    "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); "
-                                   "MEASURED_PEAKS.json has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
-                    "algorithmic_flops_per_eval": flops,
-                    "kernel": "k_walkers<0, true, false, 15> (full-model instantiation)",
-                    "note": "achieved = SURVEY 8(d) algorithmic flops x evals/s; the default kernel sums "
-                            "distant Balmer-line clusters by a far-field series and executes ~8x fewer "
-                            "flops than that count, so frac can exceed 1; exact_line_sum below is the "
-                            "kernel that executes them all",
-                    "fp64_pipe_busy_ncu": pipe_busy}
-        # HBM view, for completeness: 168 algorithmic bytes per evaluation (params in, ln-prob out)
+            prof = json.load(open(tpath))
+        launch_ms = total_ms / args.steps / 2.0                 # one launch per half
+        evals_per_s_gpu = per_gpu / (launch_ms * 1e-3)          # this GPU's kernel rate
+        exec_flops = prof.get("executed_flops_per_eval")
+        achieved = exec_flops * evals_per_s_gpu / 1e12 if exec_flops else None
+        roofline = {
+            "bound": "fp64", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
+            "frac": achieved / float(peak.value) if achieved and peak.value else None,
+            "traffic": prof.get("dram_bytes_per_launch"),
+            "kernel": "k_walkers<0, true, false, 15%s> (full-model instantiation), %d walkers per launch"
+                      % (" | parts" if world > 1 and plan_uses_parts(per_gpu) else "", per_gpu),
+            "launch_ms": launch_ms,
+            "what": "frac = FP64 flops the kernel EXECUTES per evaluation (ncu: 2 x DFMA + DADD + DMUL thread "
+                    "instructions, profiles/k_walkers_traffic.json) x evaluations/s of the launch / measured DFMA peak",
+            "executed_flops_per_eval": exec_flops,
+            "algorithmic_flops_per_eval": flops,
+            "algorithmic_ratio": flops * evals_per_s_gpu / 1e12 / float(peak.value) if peak.value else None,
+            "algorithmic_ratio_note": "SURVEY 8(d) counts every one of the 397 x P_red Lorentzians; the kernel sums "
+                                      "distant line clusters by a far-field series and reads pre-broadened template "
+                                      "rows, so it executes ~12x fewer flops than that count -- this ratio is a "
+                                      "speed-up over the naive algorithm, not a utilisation",
+            "fp64_pipe_busy_ncu": prof.get("fp64_pipe_busy_default"),
+            "peak_source": "DFMA microbenchmark measured in this run (spamm_fp64_peak_probe); MEASURED_PEAKS.json "
+                           "has no FP64 entry; nominal 148*64*2*1.965 GHz = 37.2",
+            "traffic_note": "DRAM bytes per launch from one ncu --set full capture: the 13.4 MB pre-broadened "
+                            "template bank refilled into L2 after the deliberate flush between timed steps (2.5 us "
+                            "at the measured HBM rate) + parameters in / results out; nothing is re-read"}
         hbm_peak = None
-        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(mp):
-            hbm_peak = json.load(open(mp)).get("hbm_gbs")
-        alg_bytes = 8.0 * (plan.n_dim + 1) * n_local
-        gbs = alg_bytes / (total_ms / args.steps * 1e-3) / 1e9
+        mp_ = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp_):
+            hbm_peak = json.load(open(mp_)).get("hbm_gbs")
+        alg_bytes = 8.0 * (plan.n_dim + 1) * per_gpu
+        gbs = alg_bytes / (launch_ms * 1e-3) / 1e9
         roofline["hbm_view"] = {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": gbs,
                                 "peak_gbs": hbm_peak if hbm_peak else 6650.0,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6.65 TB/s",
                                 "frac": gbs / (hbm_peak if hbm_peak else 6650.0),
-                                "note": "arithmetic intensity ~1e5 flop/B: HBM is not the bound"}
-        if exact_ms is not None:
-            ach2 = flops * (n_local / (exact_ms * 1e-3)) / 1e12
-            roofline["exact_line_sum"] = {"ms_per_step": exact_ms, "evals_per_s": n_local / (exact_ms * 1e-3),
-                                          "achieved": ach2, "frac": ach2 / float(peak.value),
-                                          "max_rel_diff_vs_default": exact_rel}
+                                "note": "arithmetic intensity ~1e4 executed flop/B: HBM is not the bound"}
+        if exact is not None:
+            ach2 = flops * exact["evals_per_s"] / 1e12
+            exact.update({"achieved": ach2, "frac": ach2 / float(peak.value),
+                          "what": "bc_exact_line_sum kernel: executes the SURVEY 8(d) flops (4096 walkers)"})
+            roofline["exact_line_sum"] = exact
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu = max(16 * cores, 128)
-            v, vals = cpu_pool_throughput(wl, np.asarray(model.data_spectrum.flux),
-                                          np.asarray(model.data_spectrum.flux_error),
-                                          params_host[:n_cpu], cores)
-            gpu_vals = res[:n_cpu]
-            rel = float(np.max(np.abs(vals - gpu_vals) / np.abs(vals)))
-            # one core, in process (SURVEY.md 8(d) asks for n = 1 and n = all cores)
-            _oracle_init(wl, np.asarray(model.data_spectrum.flux), np.asarray(model.data_spectrum.flux_error))
-            t0 = time.perf_counter()
-            for p1 in params_host[:24]:
-                _oracle_eval(p1)
-            v1 = 24.0 / (time.perf_counter() - t0)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "value_one_core": v1,
-                   "sample": "first %d walkers of the same ensemble, numpy port of the reference, "
-                             "multiprocessing.Pool(%d).map" % (n_cpu, cores),
-                   "max_rel_diff_vs_gpu": rel}
+            flux, err = np.asarray(model.data_spectrum.flux), np.asarray(model.data_spectrum.flux_error)
+            gpu_vals = np.concatenate(local_full)
+            n_port = max(16 * cores, 128)
+            v_port, vals_port = cpu_pool_throughput("port", wl, flux, err, params_host[:n_port], cores)
+            rel_port = float(np.max(np.abs(vals_port - gpu_vals[:n_port]) / np.abs(vals_port)))
+            port = {"value": v_port, "cores": cores, "walkers": n_port, "max_rel_diff_vs_gpu": rel_port,
+                    "value_one_core": cpu_one_core("port", wl, flux, err, params_host[:16])}
+            if reference_available():
+                n_ref = max(12 * cores, 96)
+                v_ref, vals_ref = cpu_pool_throughput("reference", wl, flux, err, params_host[:n_ref], cores)
+                rel_ref = float(np.max(np.abs(vals_ref - gpu_vals[:n_ref]) / np.abs(vals_ref)))
+                cpu = {"value": v_ref, "unit": UNIT, "cores": cores, "kind": "reference",
+                       "value_one_core": cpu_one_core("reference", wl, flux, err, params_host[:8]),
+                       "sample": "first %d walkers of the same ensemble through the reference's own ln_posterior "
+                                 "(spamm/Model.py:42-79, unmodified, oracle/_ref under oracle/refshim), "
+                                 "multiprocessing.Pool(%d).map" % (n_ref, cores),
+                       "max_rel_diff_vs_gpu": rel_ref, "numpy_port": port}
+            else:
+                cpu = {"value": v_port, "unit": UNIT, "cores": cores, "kind": "port",
+                       "value_one_core": port["value_one_core"],
+                       "sample": "first %d walkers of the same ensemble, numpy port of the reference (oracle/_ref "
+                                 "absent), multiprocessing.Pool(%d).map" % (n_port, cores),
+                       "max_rel_diff_vs_gpu": rel_port}
+        exchange = "none (one GPU)" if world == 1 else \
+            "walker kernel stores each result into every rank's region over NVLink (CUDA IPC) and raises a flag; " \
+            "a device-side wait for all flags follows; no collective, no host barrier"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: full NC+Fe+HG+BC, 8192 px, D=20, walkers from priors (seed 42)",
-                       "walkers_per_gpu": n_local, "walkers_total": n_local * world, "n_pix": N_PIX,
-                       "l2": "256 MiB flush between timed steps", "parallelism": "walkers sharded x%d" % world, "exchange": exchange,
+            "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "walkers_total": W, "n_pix": N_PIX,
+                       "step": "two batched half-ensemble calls (%d walkers each), each sharded over %d GPU(s)"
+                               % (Wh, world),
+                       "walkers_per_gpu_per_call": per_gpu,
+                       "l2": "256 MiB flush between timed steps", "parallelism": "walkers sharded x%d" % world,
+                       "exchange": exchange, "verified": "every rank holds the whole vector, bit-identical to the "
+                                                         "unsharded evaluation" if world > 1 else "n/a",
                        "template_mode": "bank" if plan.template_mode == _lib.TEMPLATES_BANK else "direct"},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params_host.nbytes),
-                    "d2h_bytes_per_step": int(n_local * 8), "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "what": "Model.lnposterior_batch%s with pinned host buffers, two half-ensemble calls per step"
+                            % ("_sharded" if world > 1 else "")},
             "gpu_launches": int(launches),
             "ms_per_step_minmax": [float(ms.min()), float(ms.max())],
             "secondary": secondary,
         }
         print(json.dumps(line))
+    if ex is not None:
+        ex.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def plan_uses_parts(n):
+    """Mirror of the library's automatic choice (spamm_b200.cu parts_for): two CTAs per walker between half a
+    wave and a wave and a half of CTAs."""
+    slots = 148 * 4
+    return 2 * n > slots and n <= 3 * slots // 2
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--walkers", type=int, default=N_WALKERS, help="walkers per GPU (weak) / total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--walkers", type=int, default=N_WALKERS, help="walkers of the (one) ensemble")
+    ap.add_argument("--sustained", type=float, default=5.0, help="seconds of the sustained leg (0: skip; N = 1 only)")
+    ap.add_argument("--sampler-iterations", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
-    ap.add_argument("--no-sampler", action="store_true", help="skip the half-step / device-sampler figures")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: how per-walker ln-probs reach every rank")
+    ap.add_argument("--no-sampler", action="store_true", help="skip the device-sampler figure")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling figure")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

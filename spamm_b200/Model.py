@@ -94,6 +94,7 @@ class Model(object):
         """Pickle without the device plan (rebuilt on demand after loading)."""
         d = dict(self.__dict__)
         d["_plan"] = None
+        d.pop("_exchange", None)
         return d
 
     # -- sampler -----------------------------------------------------------------------
@@ -164,6 +165,20 @@ class Model(object):
             ln_p += sum(component.ln_priors(params=p[0:component.parameter_count]))
             p = p[component.parameter_count:]
         return ln_p
+
+    def lnposterior_batch_sharded(self, params, out=None):
+        """`lnposterior_batch` with the ensemble sharded over the ranks of torch.distributed (one process per
+        GPU): `params` is the same [W, D] array on every rank, each rank uploads and evaluates only its
+        slice, the walker kernel stores the results into every rank's exchange region over NVLink, and every
+        rank returns the whole [W] vector.  Collective: all ranks must call it together.  (This is what
+        replaces emcee's pool.map task farm, Model.py:264-289.)"""
+        from .distributed import world_info
+        if world_info()[1] == 1:
+            return self.plan.lnposterior_host(params, out=out)
+        if getattr(self, "_exchange", None) is None:
+            from .distributed import Exchange
+            self._exchange = Exchange(self.max_walkers)
+        return self.plan.lnposterior_sharded_host(params, self._exchange, out=out)
 
     def lnposterior_batch(self, params, out=None):
         """ln-posterior of a whole walker ensemble in one call: numpy [W, D] -> numpy [W]

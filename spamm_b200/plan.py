@@ -133,18 +133,21 @@ class ModelPlan(object):
         the plan does not hold (its ln-posterior would be wrong, not -inf); clears the condition."""
         _lib.check(self.lib.spamm_plan_check(self._h, self._stream()))
 
-    def lnposterior_sharded(self, params, exchange, out=None):
+    def lnposterior_sharded(self, params, exchange, out=None, copy=True):
         """Multi-GPU form of `lnposterior`: params is the full replicated [n, D] tensor; this rank
         evaluates its slice and the kernel stores the results into every rank's exchange region.
-        Returns the gathered [n] vector (a copy in `out`), complete in stream order."""
+        Returns the gathered [n] vector (a copy in `out`), complete in stream order.  copy=False leaves
+        the vector in the exchange region only (what the library's own sampler loop consumes) and
+        returns None."""
         torch = _torch()
         self._check_params(params)
         n = params.shape[0]
-        if out is None:
+        if copy and out is None:
             out = torch.empty(n, dtype=torch.float64, device=params.device)
         _lib.check(self.lib.spamm_lnpost_batch_sharded(self._h, exchange._h, ctypes.c_void_p(params.data_ptr()), n,
-                                                       ctypes.c_void_p(out.data_ptr()), None, self._stream()))
-        return out
+                                                       ctypes.c_void_p(out.data_ptr()) if copy else None, None,
+                                                       self._stream()))
+        return out if copy else None
 
     def lnposterior_sharded_host(self, params, exchange, out=None):
         """numpy [n, D] (the same array on every rank) -> numpy [n]: H2D of this rank's rows, kernel +
