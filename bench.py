@@ -10,8 +10,9 @@ one stretch-move iteration of that ensemble: two batched calls of one half-ensem
 the stretch move updates the halves alternately, so a half is the largest batch a sampler can hand over --
 with the parameters already resident in HBM.  On N > 1 GPUs every half is sharded N ways (strong scaling:
 the ensemble does not grow) and each call ends with the per-walker results on EVERY rank: the walker kernel
-stores them into all ranks' exchange regions over NVLink and raises a flag, and a wait for all flags is
-queued behind it (include/spamm_b200.h, "multi-GPU").  `value` = 8192 * K / time, timed with CUDA events,
+leaves them in its rank's exchange region and raises a flag in all ranks' regions over NVLink, and the
+gather kernel queued behind it waits for all flags and pulls the other ranks' slices (include/spamm_b200.h,
+"multi-GPU").  `value` = 8192 * K / time, timed with CUDA events,
 max over ranks.  One JSON line is printed by rank 0.
 """
 import argparse
@@ -266,6 +267,8 @@ def run_ours(args):
     from spamm_b200.distributed import init_from_env, Exchange
     from spamm_b200.synth import full_model_workload
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"                # stdout carries one JSON line, not NCCL's version banner
     rank, world, local_rank = init_from_env("nccl")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -567,8 +570,9 @@ def run_ours(args):
                                  "absent), multiprocessing.Pool(%d).map" % (n_port, cores),
                        "max_rel_diff_vs_gpu": rel_port}
         exchange = "none (one GPU)" if world == 1 else \
-            "walker kernel stores each result into every rank's region over NVLink (CUDA IPC) and raises a flag; " \
-            "a device-side wait for all flags follows; no collective, no host barrier"
+            "walker kernel leaves its results in its rank's region (CUDA IPC mapped) and raises a flag in every " \
+            "rank's region over NVLink; a gather kernel waits for all flags and pulls the peers' slices; " \
+            "no collective, no host barrier"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,

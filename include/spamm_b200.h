@@ -144,15 +144,6 @@ void spamm_plan_destroy(SpammPlan* plan);
 int spamm_lnpost_batch(SpammPlan* plan, const double* params_dev, int32_t n_walkers,
                        double* lnp_dev, void* stream);
 
-/* Multi-GPU variant with the result exchange fused into the kernel: walker w's ln-posterior
- * is stored at element (elem_offset + w) of EVERY buffer in peer_bufs_dev[0..n_peers) -- the
- * symmetric, peer-mapped buffers of all ranks (this rank included) -- by P2P stores over
- * NVLink, so no all-gather copy follows; the caller only needs a cross-rank barrier before it
- * reads its own buffer.  Replaces the result gather of emcee's pool.map (Model.py:267-286). */
-int spamm_lnpost_batch_p2p(SpammPlan* plan, const double* params_dev, int32_t n_walkers,
-                           const uint64_t* peer_bufs_dev, int32_t n_peers, int64_t elem_offset,
-                           void* stream);
-
 /* Same call with HOST buffers: pinned staging, H2D, kernel, D2H, synchronise.
  * This is what an emcee `pool.map` adapter binds (Model.py:283-289).
  * Returns SPAMM_ERANGE (and clears the condition) if any walker set the device status word. */
@@ -237,10 +228,11 @@ int spamm_stretch_run(SpammPlan* plan, double* walkers_dev, double* lnp_dev, int
 /* ---- multi-GPU: walker shards, results exchanged by the compute kernel itself -------------------
  * Replaces the task farm of emcee's pool (spamm/Model.py:264-289: pickled (Model, params) tasks out,
  * floats back).  Every rank holds the replicated ensemble and the same counter-based RNG; a sharded call
- * evaluates walkers [lo, hi) = spamm_shard_bounds(n, n_ranks, rank) on this rank, and the walker kernel
- * stores each ln-posterior directly into EVERY rank's exchange region (peer-to-peer stores over NVLink)
- * and, when its last walker retires, raises this rank's flag in every region.  Consumers wait on the
- * flags on the device; there is no host-side barrier and no collective on the data path.
+ * evaluates walkers [lo, hi) = spamm_shard_bounds(n, n_ranks, rank) on this rank: the walker kernel leaves
+ * each ln-posterior in this rank's exchange region and, when its last walker retires, raises this rank's
+ * flag in EVERY rank's region (release stores over NVLink).  Consumers (the gather kernel, the sampler's
+ * accept kernel) wait on the flags on the device and pull the other ranks' entries straight out of their
+ * regions (peer loads over NVLink); there is no host-side barrier and no collective on the data path.
  * All ranks must make the same sequence of sharded calls (the epoch counter is implicit). */
 typedef struct SpammExchange SpammExchange;
 #define SPAMM_IPC_HANDLE_BYTES 64
@@ -264,9 +256,10 @@ void spamm_exchange_destroy(SpammExchange* ex);
 
 /* spamm_lnpost_batch over a sharded ensemble: params_dev is the FULL replicated [n_total][D] array
  * (only this rank's rows are read).  Queues on `stream`: the walker kernel on this rank's slice (results
- * and flag to every rank), then a wait for every rank's flag, then -- if lnp_dev != NULL -- a copy of the
- * gathered [n_total] vector to lnp_dev.  *lnp_region_out (may be NULL) is the vector inside this rank's
- * region; it stays valid until the second-next sharded call. */
+ * into this rank's region, flag to every rank), then the gather kernel: wait for every rank's flag, pull
+ * the other ranks' slices, and -- if lnp_dev != NULL -- write the gathered [n_total] vector to lnp_dev too.
+ * *lnp_region_out (may be NULL) is the vector inside this rank's region; it stays valid until the
+ * second-next sharded call. */
 int spamm_lnpost_batch_sharded(SpammPlan* plan, SpammExchange* ex, const double* params_dev, int32_t n_total,
                                double* lnp_dev, const double** lnp_region_out, void* stream);
 /* Host-buffer form: H2D of this rank's parameter rows only, kernel + exchange, D2H of the whole gathered
@@ -274,7 +267,8 @@ int spamm_lnpost_batch_sharded(SpammPlan* plan, SpammExchange* ex, const double*
 int spamm_lnpost_batch_sharded_host(SpammPlan* plan, SpammExchange* ex, const double* params_host,
                                     int32_t n_total, double* lnp_host);
 /* spamm_stretch_run with every half-step's proposals sharded over the ranks: propose (replicated), walker
- * kernel on this rank's slice (P2P stores + flag), accept after the flag wait inside the accept kernel.
+ * kernel on this rank's slice (+ flag), accept after the flag wait inside the accept kernel, which pulls
+ * each proposal's ln-posterior from the rank that evaluated it.
  * Chains are bit-identical to the single-device run with the same seed. */
 int spamm_stretch_run_sharded(SpammPlan* plan, SpammExchange* ex, double* walkers_dev, double* lnp_dev,
                               int32_t n_walkers, double a, uint64_t seed, uint64_t iter0, int32_t n_iter,

@@ -81,7 +81,7 @@ class SpammPlanDesc(ctypes.Structure):
 
 # every symbol include/spamm_b200.h declares
 EXPORTS = [
-    "spamm_plan_create", "spamm_plan_destroy", "spamm_lnpost_batch", "spamm_lnpost_batch_host", "spamm_lnpost_batch_p2p",
+    "spamm_plan_create", "spamm_plan_destroy", "spamm_lnpost_batch", "spamm_lnpost_batch_host",
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
     "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split", "spamm_plan_specialised",
     "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record", "spamm_stretch_run",
@@ -128,8 +128,6 @@ def load():
     lib.spamm_plan_destroy.restype = None
     lib.spamm_lnpost_batch.argtypes = [vp, vp, i32, vp, vp]
     lib.spamm_lnpost_batch.restype = ctypes.c_int
-    lib.spamm_lnpost_batch_p2p.argtypes = [vp, vp, i32, vp, i32, i64, vp]
-    lib.spamm_lnpost_batch_p2p.restype = ctypes.c_int
     lib.spamm_lnpost_batch_host.argtypes = [vp, vp, i32, vp]
     lib.spamm_lnpost_batch_host.restype = ctypes.c_int
     lib.spamm_model_flux_batch.argtypes = [vp, u32, vp, i32, vp, vp]

@@ -48,16 +48,14 @@ __global__ void k_stretch_propose(const double* __restrict__ walkers, int K, int
     z[i] = zz;
 }
 
-// flags != nullptr (multi-GPU): lnp_q is this rank's exchange buffer, filled by every rank's walker kernel
-// over NVLink; each block first waits until all ranks have raised their flag for `epoch` (wait_flags) and
-// reads the values past L1.
+// pi.bufs != nullptr (multi-GPU): lnp_q is unused; every rank's walker kernel has left its slice of the
+// proposals' ln-posteriors in its own exchange region.  Each block waits until all ranks have raised their
+// flag for the epoch and a thread takes its walker's value from the owner's region (wait_flags, gathered_value).
 __global__ void k_stretch_accept(double* __restrict__ walkers, double* __restrict__ lnp, int K,
                                  int D, int half, const double* __restrict__ q,
                                  const double* __restrict__ z, const double* lnp_q,
-                                 uint64_t seed, uint64_t iter, long long* __restrict__ nacc,
-                                 const unsigned long long* flags, int n_peers, unsigned long long epoch,
-                                 int* status, int* status_host) {
-    if (flags != nullptr) wait_flags(flags, n_peers, epoch, status, status_host);
+                                 uint64_t seed, uint64_t iter, long long* __restrict__ nacc, PeerIn pi) {
+    if (pi.bufs != nullptr) wait_flags(pi);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int Ns = K / 2;
     if (i >= Ns) return;
@@ -66,7 +64,7 @@ __global__ void k_stretch_accept(double* __restrict__ walkers, double* __restric
                (uint32_t)iter, (uint32_t)(iter >> 32) ^ 0x41434350u, r);
     double u = u53(r[0], r[1]);
     int wi = half == 0 ? i : Ns + i;
-    const double lq = __ldcg(lnp_q + i);
+    const double lq = pi.bufs != nullptr ? gathered_value(pi, i) : lnp_q[i];
     double lnpdiff = ((double)D - 1.0) * log(z[i]) + lq - lnp[wi];
     if (lnpdiff > log(u)) {
         for (int d = 0; d < D; ++d) walkers[(size_t)wi * D + d] = q[(size_t)i * D + d];

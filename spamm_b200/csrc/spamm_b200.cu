@@ -902,18 +902,6 @@ extern "C" int spamm_lnpost_batch(SpammPlan* pl, const double* params_dev, int32
     return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, lnp_dev, (cudaStream_t)stream, false);
 }
 
-extern "C" int spamm_lnpost_batch_p2p(SpammPlan* pl, const double* params_dev, int32_t n_walkers,
-                                      const uint64_t* peer_bufs_dev, int32_t n_peers, int64_t elem_offset,
-                                      void* stream) {
-    if (!pl || !params_dev || !peer_bufs_dev) return set_error(SPAMM_EINVAL, "null argument");
-    if (n_walkers < 0 || n_peers < 1 || elem_offset < 0) return set_error(SPAMM_EINVAL, "bad argument");
-    if (n_walkers == 0) return SPAMM_OK;
-    if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
-    PeerOut po{reinterpret_cast<const unsigned long long*>(peer_bufs_dev), n_peers, (long long)elem_offset,
-               nullptr, 0u, 0, 0ull};
-    return launch_walkers<0>(pl, full_mask(pl), params_dev, n_walkers, nullptr, (cudaStream_t)stream, false, po);
-}
-
 extern "C" int spamm_lnpost_batch_host(SpammPlan* pl, const double* params_host, int32_t n_walkers,
                                        double* lnp_host) {
     if (!pl || !params_host || !lnp_host) return set_error(SPAMM_EINVAL, "null argument");
@@ -1024,7 +1012,7 @@ extern "C" int spamm_stretch_accept(double* walkers_dev, double* lnp_dev, int32_
     int Ns = K / 2;
     k_stretch_accept<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed, iteration,
-        reinterpret_cast<long long*>(naccepted_dev), nullptr, 0, 0ull, nullptr, nullptr);
+        reinterpret_cast<long long*>(naccepted_dev), PeerIn{nullptr, 0, 0, 0, 1, 0ull, nullptr, nullptr});
     CUDA_TRY(cudaGetLastError());
     return SPAMM_OK;
 }
@@ -1144,7 +1132,7 @@ static int exchange_create_impl(SpammExchange* ex, int32_t n_ranks, int32_t rank
     // that peer (another stream of this process) is the one stuck loading.
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_raise_flags));
-    CUDA_TRY(cudaFuncGetAttributes(&fa, k_wait_flags));
+    CUDA_TRY(cudaFuncGetAttributes(&fa, k_gather));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_stretch_propose));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_stretch_accept));
     CUDA_TRY(cudaFuncGetAttributes(&fa, k_chain_record));
@@ -1199,10 +1187,10 @@ extern "C" int spamm_exchange_connect_ptrs(SpammExchange* ex, const uint64_t* re
 extern "C" uint64_t spamm_exchange_region_ptr(const SpammExchange* ex) { return ex ? (uint64_t)ex->region : 0; }
 extern "C" uint64_t spamm_exchange_epoch(const SpammExchange* ex) { return ex ? ex->epoch : 0; }
 
-// queue one sharded evaluation of params_dev[n_total][D]: this rank's slice through k_walkers with P2P stores
-// and the flag raise; returns the epoch's buffer in this rank's region (complete once every flag >= epoch)
+// queue one sharded evaluation of params_dev[n_total][D]: this rank's slice through k_walkers, results into this
+// rank's region, flag raised in every region; *pi_out tells a consumer where the gathered vector lives
 static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_dev, int32_t n_total,
-                        cudaStream_t st, const double** buf_out, uint64_t* epoch_out) {
+                        cudaStream_t st, PeerIn* pi_out) {
     if (!ex->connected) return set_error(SPAMM_EINVAL, "exchange is not connected");
     if (n_total > ex->max_n) return set_error(SPAMM_EINVAL, "exchange region holds fewer walkers than n_total");
     const uint64_t e = ++ex->epoch;
@@ -1219,8 +1207,18 @@ static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_d
         pl->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
-    *buf_out = reinterpret_cast<const double*>(ex->region) + boff;
-    *epoch_out = e;
+    *pi_out = PeerIn{ex->d_peer_ptrs, ex->n_ranks, ex->rank, boff, (int)((n_total + ex->n_ranks - 1) / ex->n_ranks), e,
+                     pl->dev.status, pl->dev.status_host};
+    return SPAMM_OK;
+}
+
+// wait for every rank's flag and pull the other ranks' slices into this rank's region (and into `copy`)
+static int queue_gather(SpammPlan* pl, SpammExchange* ex, const PeerIn& pi, int32_t n_total, double* copy,
+                        cudaStream_t st) {
+    k_gather<<<(n_total + 255) / 256, 256, 0, st>>>(pi, n_total, copy);
+    pl->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    (void)ex;
     return SPAMM_OK;
 }
 
@@ -1231,17 +1229,12 @@ extern "C" int spamm_lnpost_batch_sharded(SpammPlan* pl, SpammExchange* ex, cons
     if (n_total < 1) return set_error(SPAMM_EINVAL, "need at least one walker");
     if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
     cudaStream_t st = (cudaStream_t)stream;
-    const double* buf = nullptr;
-    uint64_t e = 0;
+    PeerIn pi;
     int rc = deferred_status(pl, st);
     if (rc) return rc;
-    if ((rc = sharded_eval(pl, ex, params_dev, n_total, st, &buf, &e))) return rc;
-    k_wait_flags<<<1, kFlagWords, 0, st>>>(reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e,
-                                           pl->dev.status, pl->dev.status_host);
-    pl->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    if (lnp_dev) CUDA_TRY(cudaMemcpyAsync(lnp_dev, buf, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    if (lnp_region_out) *lnp_region_out = buf;
+    if ((rc = sharded_eval(pl, ex, params_dev, n_total, st, &pi))) return rc;
+    if ((rc = queue_gather(pl, ex, pi, n_total, lnp_dev, st))) return rc;
+    if (lnp_region_out) *lnp_region_out = reinterpret_cast<const double*>(ex->region) + pi.boff;
     return SPAMM_OK;
 }
 
@@ -1272,16 +1265,14 @@ extern "C" int spamm_lnpost_batch_sharded_host(SpammPlan* pl, SpammExchange* ex,
         if (!is_pinned(params_host)) { memcpy(ex->h_params, src, nb); src = ex->h_params; }
         CUDA_TRY(cudaMemcpyAsync(ex->d_params + (size_t)lo * D, src, nb, cudaMemcpyHostToDevice, st));
     }
-    const double* buf = nullptr;
-    uint64_t e = 0;
-    int rc = sharded_eval(pl, ex, ex->d_params, n_total, st, &buf, &e);
+    PeerIn pi;
+    int rc = sharded_eval(pl, ex, ex->d_params, n_total, st, &pi);
     if (rc) return rc;
-    k_wait_flags<<<1, kFlagWords, 0, st>>>(reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e,
-                                           pl->dev.status, pl->dev.status_host);
-    pl->launches += 1;
+    if ((rc = queue_gather(pl, ex, pi, n_total, nullptr, st))) return rc;
     const bool pin_out = is_pinned(lnp_host);
     double* dst = pin_out ? lnp_host : ex->h_lnp;
-    CUDA_TRY(cudaMemcpyAsync(dst, buf, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(dst, reinterpret_cast<const double*>(ex->region) + pi.boff,
+                             (size_t)n_total * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!pin_out) memcpy(lnp_host, ex->h_lnp, (size_t)n_total * sizeof(double));
     return check_status(pl, st);
@@ -1307,14 +1298,11 @@ extern "C" int spamm_stretch_run_sharded(SpammPlan* pl, SpammExchange* ex, doubl
         for (int half = 0; half < 2; ++half) {
             int rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream);
             if (rc) return rc;
-            const double* buf = nullptr;
-            uint64_t e = 0;
-            if ((rc = sharded_eval(pl, ex, q_dev, Ns, st, &buf, &e))) return rc;
+            PeerIn pi;
+            if ((rc = sharded_eval(pl, ex, q_dev, Ns, st, &pi))) return rc;
             k_stretch_accept<<<(Ns + 127) / 128, 128, 0, st>>>(
-                walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, buf, seed, iteration,
-                reinterpret_cast<long long*>(naccepted_dev),
-                reinterpret_cast<const unsigned long long*>(ex->region), ex->n_ranks, e, pl->dev.status,
-                pl->dev.status_host);
+                walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, nullptr, seed, iteration,
+                reinterpret_cast<long long*>(naccepted_dev), pi);
             CUDA_TRY(cudaGetLastError());
         }
         if (chain_dev || lnp_chain_dev) {

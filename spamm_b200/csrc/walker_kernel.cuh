@@ -20,21 +20,37 @@ struct TemplCoef {
     double a;          // norm_t / nf
 };
 
-// Multi-GPU result exchange fused into the kernel: instead of writing lnp[w] locally and
-// all-gathering afterwards, the finishing thread stores the value straight into every peer's
-// region over NVLink (P2P stores); bufs == nullptr selects the plain local store.
-// With done_cnt set the kernel also signals: the CTA that retires the launch's last walker raises
-// this rank's flag (word `rank` of every peer's flag block, value `epoch`) after a system-scope
-// fence, so a consumer on any rank that has seen flag >= epoch (k_wait_flags, k_stretch_accept) sees
-// all of this rank's results -- no host-side barrier, no collective.
+// Multi-GPU result exchange.  Every rank owns an exchange REGION (plan_dev.cuh: kFlagWords flag words, then
+// two result buffers) that all peers have mapped (CUDA IPC / NVLink).  A sharded call works like this:
+//   producer  k_walkers stores each of its walkers' results into its OWN region (bufs != nullptr selects
+//             that instead of out[w]), fences at device scope and counts the walker; the thread that retires
+//             the call's last walker fences at system scope and raises this rank's flag -- word `rank` of
+//             EVERY rank's flag block, value `epoch` -- with release stores over NVLink.
+//   consumer  (k_gather, k_stretch_accept) waits until every rank's flag in its own region has reached the
+//             epoch, then PULLS the entries other ranks own straight out of their regions (peer loads).
+// No per-walker traffic or system fence on the producer side, no collective, no host barrier.
+// (Measured alternatives, profiles/r02_experiments.txt: per-walker P2P stores + system fence from every
+//  finishing thread cost 19 us per call on 2 GPUs -- the fence's NVLink round trip delays every CTA's exit;
+//  a push of the whole slice by the last CTA 29 us.)
 struct PeerOut {
-    const unsigned long long* bufs;   // device array of n_peers base pointers (incl. this rank)
+    const unsigned long long* bufs;   // device array of n_peers region base pointers (incl. this rank's); null: out[w]
     int n_peers;
     long long offset;                 // element offset of this launch's walker 0 from a base pointer
-    unsigned* done_cnt;               // device counter of retired walkers (null: no signalling)
+    unsigned* done_cnt;               // device counter of retired walkers
     unsigned n_done;                  // walkers of the whole sharded call (may span several launches)
-    int rank;                         // this rank's flag word
+    int rank;                         // this rank
     unsigned long long epoch;         // value to raise
+};
+
+// what a consumer needs to find walker i of the gathered vector: rank i / per owns it
+struct PeerIn {
+    const unsigned long long* bufs;   // region base pointers; null: single-device call, nothing to wait for
+    int n_peers, rank;
+    long long boff;                   // element offset of the epoch's result buffer in a region
+    int per;                          // walkers per rank (spamm_shard_bounds)
+    unsigned long long epoch;
+    int* status;
+    int* status_host;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -45,8 +61,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// raise this rank's flag in every peer's flag block (the first kFlagWords words of a region)
+// raise this rank's flag in every rank's flag block
 __device__ __forceinline__ void raise_flags(const PeerOut& po) {
     __threadfence_system();
     for (int r = 0; r < po.n_peers; ++r)
@@ -55,42 +81,50 @@ __device__ __forceinline__ void raise_flags(const PeerOut& po) {
 
 __device__ __forceinline__ void store_result(double* out, int w, double v, const PeerOut& po) {
     if (po.bufs == nullptr) { out[w] = v; return; }
-    for (int r = 0; r < po.n_peers; ++r)
-        reinterpret_cast<double*>(po.bufs[r])[po.offset + w] = v;
-    if (po.done_cnt != nullptr) {
-        __threadfence_system();                                   // results before the count
-        if (atomicAdd(po.done_cnt, 1u) + 1u == po.n_done) {       // this walker retires the call
-            *po.done_cnt = 0u;
-            raise_flags(po);
-        }
+    reinterpret_cast<double*>(po.bufs[po.rank])[po.offset + w] = v;
+    __threadfence();                                              // the result before the count
+    if (atomicAdd(po.done_cnt, 1u) + 1u == po.n_done) {           // this walker retires the call
+        *po.done_cnt = 0u;
+        raise_flags(po);
     }
 }
 
 // a rank without walkers in a sharded call still has to raise its flag
 __global__ void k_raise_flags(PeerOut po) { raise_flags(po); }
 
-// Spin until every rank's flag in this rank's flag block has reached `epoch` (threads 0..n_peers-1 of the
-// calling block); gives up after ~5 s and sets kStatPeerTimeout so a lost peer cannot hang the device.
-__device__ __forceinline__ void wait_flags(const unsigned long long* flags, int n_peers, unsigned long long epoch,
-                                           int* status, int* status_host) {
-    if ((int)threadIdx.x < n_peers) {
-        unsigned long long t0 = 0;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+// Consumer side, called by every thread of a block: threads 0..n_peers-1 spin until rank r's flag in this
+// rank's flag block has reached the epoch; gives up after ~5 s and sets kStatPeerTimeout so a lost peer
+// cannot hang the device.
+__device__ __forceinline__ void wait_flags(const PeerIn& pi) {
+    if ((int)threadIdx.x < pi.n_peers) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(pi.bufs[pi.rank]) + threadIdx.x;
+        const unsigned long long t0 = global_timer_ns();
         unsigned spins = 0;
-        while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
-            if ((++spins & 1023u) == 0u) {
-                unsigned long long t1;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 5000000000ull) { flag_status(status, status_host, kStatPeerTimeout); break; }
+        while (ld_acquire_sys(flag) < pi.epoch) {
+            if ((++spins & 1023u) == 0u && global_timer_ns() - t0 > 5000000000ull) {
+                flag_status(pi.status, pi.status_host, kStatPeerTimeout);
+                break;
             }
         }
     }
     __syncthreads();
 }
 
-__global__ void k_wait_flags(const unsigned long long* flags, int n_peers, unsigned long long epoch, int* status,
-                             int* status_host) {
-    wait_flags(flags, n_peers, epoch, status, status_host);
+// entry i of the gathered vector, after wait_flags: from this rank's region or pulled from the owner's
+__device__ __forceinline__ double gathered_value(const PeerIn& pi, int i) {
+    const int owner = i / pi.per;
+    const double* src = reinterpret_cast<const double*>(pi.bufs[owner]) + pi.boff + i;
+    return owner == pi.rank ? __ldcg(src) : ld_volatile_f64(src);
+}
+
+// complete the gathered vector of a sharded call in this rank's region (and in `copy`, if given)
+__global__ void __launch_bounds__(256) k_gather(PeerIn pi, int n_total, double* __restrict__ copy) {
+    wait_flags(pi);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    const double v = gathered_value(pi, i);
+    if (i / pi.per != pi.rank) reinterpret_cast<double*>(pi.bufs[pi.rank])[pi.boff + i] = v;
+    if (copy != nullptr) copy[i] = v;
 }
 
 // Walker PARTS (kSpecParts instantiations): a walker is evaluated by two independent CTAs -- the "red" part

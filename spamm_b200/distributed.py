@@ -6,8 +6,9 @@ Here every rank holds the full replicated sampler state and an identical
 counter-based RNG, so proposals are generated redundantly and *no parameters
 travel*; each rank evaluates its contiguous slice of the active half-ensemble
 and the only exchange is the per-walker ln-probabilities of each stretch half-step.
-On GPUs the walker kernel itself stores them into every rank's exchange region over
-NVLink and raises a flag (`Exchange`, `ExchangeLnPost`; include/spamm_b200.h
+On GPUs the walker kernel leaves them in its rank's exchange region and raises a flag
+in every rank's region over NVLink; consumers wait on the flags on the device and pull
+the other ranks' entries (`Exchange`, `ExchangeLnPost`; include/spamm_b200.h
 "multi-GPU"); `ShardedLnPost` is the collective form of the same contract
 (all-gather: NCCL, or gloo in the CPU tests).
 """
@@ -88,8 +89,8 @@ class Exchange(object):
 
     The library allocates the region (flag block + two result buffers), this wrapper all-gathers the
     64-byte CUDA IPC handles over torch.distributed and lets the library map every peer's region; from
-    then on the data path has no collective and no host barrier: the walker kernel stores each
-    ln-posterior into every rank's region over NVLink and raises a flag, consumers wait on the device.
+    then on the data path has no collective and no host barrier: the walker kernel raises a flag in every
+    rank's region over NVLink, consumers wait on the device and pull the other ranks' results.
     All ranks must make the same sequence of sharded calls."""
 
     def __init__(self, max_walkers, group=None):

@@ -135,7 +135,7 @@ class ModelPlan(object):
 
     def lnposterior_sharded(self, params, exchange, out=None, copy=True):
         """Multi-GPU form of `lnposterior`: params is the full replicated [n, D] tensor; this rank
-        evaluates its slice and the kernel stores the results into every rank's exchange region.
+        evaluates its slice; the gather kernel behind it pulls the other ranks' slices over NVLink.
         Returns the gathered [n] vector (a copy in `out`), complete in stream order.  copy=False leaves
         the vector in the exchange region only (what the library's own sampler loop consumes) and
         returns None."""
@@ -161,14 +161,6 @@ class ModelPlan(object):
         _lib.check(self.lib.spamm_lnpost_batch_sharded_host(self._h, exchange._h, p.ctypes.data_as(ctypes.c_void_p),
                                                             p.shape[0], out.ctypes.data_as(ctypes.c_void_p)))
         return out
-
-    def lnposterior_p2p(self, params, peer_bufs_dev, n_peers, elem_offset):
-        """Evaluate [W, D] walkers and store each result at elem_offset + w of every peer
-        buffer (device array of n_peers pointers); see spamm_lnpost_batch_p2p."""
-        self._check_params(params)
-        _lib.check(self.lib.spamm_lnpost_batch_p2p(self._h, ctypes.c_void_p(params.data_ptr()),
-                                                   params.shape[0], ctypes.c_void_p(int(peer_bufs_dev)),
-                                                   int(n_peers), int(elem_offset), self._stream()))
 
     def model_flux(self, params, mask=None, out=None):
         """[W, D] -> model flux [W, P] of the components selected by `mask` (all by default)."""

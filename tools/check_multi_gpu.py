@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """torchrun --nproc-per-node N tools/check_multi_gpu.py
-Sharded ln-posterior + device sampler over N GPUs (CUDA IPC exchange regions, P2P stores + flags from
+Sharded ln-posterior + device sampler over N GPUs (CUDA IPC exchange regions, flags raised by
 the walker kernel): every rank must hold the WHOLE gathered vector, bit-identical to the single-rank
 evaluation; every rank must end with the identical chain, and it must equal the chain one GPU produces
 with the same seed -- also when each rank was handed a different seed and start state (rank 0's win)."""
