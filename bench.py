@@ -475,6 +475,61 @@ def run_ours(args):
                                   "clocks": cs.stop(tw0, tw1)}
         plan.check()
 
+    # ---- the broadening kernels on the record (north_star: "a Fe-template Gaussian broadening kernel ... applies a
+    # per-walker kernel width"): BASELINE config 2 (NC + Fe, 1024 walkers x 4096 px) with the templates broadened
+    # PER WALKER inside the call (template_mode DIRECT) beside the default pre-broadened bank, and k_conv_rows /
+    # k_interp_rows timed alone against their rooflines
+    if world == 1 and not args.no_broadening:
+        from spamm_b200.synth import build_model
+        m_b, p_b = full_model_workload(4096, 1024, seed=42, components=("PL", "FE"))
+        ds = m_b.data_spectrum
+        m_d = build_model(["PL", "FE"], np.asarray(ds.spectral_axis), np.asarray(ds.flux), np.asarray(ds.flux_error),
+                          max_walkers=1024, template_mode=_lib.TEMPLATES_DIRECT)
+        pb = torch.from_numpy(p_b).to(dev)
+        ob = torch.empty(1024, dtype=torch.float64, device=dev)
+        res = {}
+        for name, mm in (("bank", m_b), ("direct", m_d)):
+            for _ in range(3):
+                mm.plan.lnposterior(pb, out=ob)
+            evb = _events(5)
+            for e0, e1 in evb:
+                flush.zero_()
+                e0.record()
+                mm.plan.lnposterior(pb, out=ob)
+                e1.record()
+            torch.cuda.synchronize()
+            res[name] = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evb]))
+            res[name + "_values"] = ob.cpu().numpy().copy()
+        assert np.array_equal(res["bank_values"], res["direct_values"]), "bank and direct broadening disagree"
+        hbm = 6465.2
+        mp_ = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp_):
+            hbm = json.load(open(mp_)).get("hbm_gbs", hbm)
+        probes = []
+        for sig in (8, 30, 60):
+            cms, ims, fma = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+            _lib.check(lib.spamm_broadening_probe(m_d.plan._h, 0, sig, 3072, 5, ctypes.byref(cms), ctypes.byref(ims),
+                                                  ctypes.byref(fma)))
+            tfl = 2.0 * fma.value / (cms.value * 1e-3) / 1e12
+            n_pts = (4181 + 584 + 4000) / 3.0
+            byt = 3072 * (n_pts * 8 + 4096 * 8)
+            probes.append({"sigma_norm": sig, "taps": 3 * sig, "rows": 3072,
+                           "k_conv_rows": {"ms": cms.value, "tflops": tfl, "frac_of_dfma_peak": tfl / float(peak.value)},
+                           "k_interp_rows+k_norm_rows": {"ms": ims.value, "gbs": byt / (ims.value * 1e-3) / 1e9,
+                                                         "frac_of_hbm_peak": byt / (ims.value * 1e-3) / 1e9 / hbm}})
+        secondary["broadening"] = {
+            "config2": {"workload": "NC + Fe, 1024 walkers x 4096 px (BASELINE config 2)",
+                        "bank_ms": res["bank"], "direct_ms": res["direct"],
+                        "direct_evals_per_s": 1024 / (res["direct"] * 1e-3),
+                        "bit_identical": True,
+                        "what": "direct = k_rows_from_params + k_conv_rows + k_interp_rows + k_norm_rows per call "
+                                "(3072 rows), then k_walkers; asynchronous (kernel widths bounded by the width prior)"},
+            "kernels": probes,
+            "rooflines": "k_conv_rows: FP64 (2 flop per tap and point, direct convolution on the ln-lambda grid) "
+                         "against the DFMA peak measured in this run; k_interp_rows: HBM (reads the convolved row, "
+                         "writes P doubles) against MEASURED_PEAKS.json hbm_gbs"}
+        del m_b, m_d
+
     # ---- weak scaling (secondary): 8192 walkers per GPU in one sharded call
     if world > 1 and not args.no_weak:
         exw = Exchange(W * world)
@@ -623,6 +678,7 @@ def main():
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
     ap.add_argument("--no-sampler", action="store_true", help="skip the device-sampler figure")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling figure")
+    ap.add_argument("--no-broadening", action="store_true", help="skip the broadening-kernel figures (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SPAMM_ABI_VERSION 3
+#define SPAMM_ABI_VERSION 4
 #define SPAMM_MAX_COMPONENTS 8
 #define SPAMM_MAX_TEMPLATES 16
 #define SPAMM_SH95_NE 7
@@ -72,6 +72,14 @@ typedef struct SpammTemplateSet {
     double sqrt_2pi;                           /* np.sqrt(2*math.pi), Fe:293 */
     int32_t kernel_size_sigma;                 /* fe_kernel_size_sigma / hg_kernel_size_sigma */
     int32_t clamp_edges;                       /* 0: np.interp(left=0,right=0) (Fe:315-319); 1: edge clamp (HG:323-325) */
+    /* rebin_spec: True (parameters.yaml; FeComponent.py:320-323 / HostGalaxyComponent.py:326-329): the
+     * convolved row goes onto the data grid by the flux-conserving rebin instead of np.interp.  The rebin is
+     * linear, so the host hands over its matrix per template in CSR form: rebin_indptr is
+     * [n_templates][P + 1] with offsets into rebin_index / rebin_weight (template-local column indices).
+     * All NULL: np.interp (the default, rebin_spec: False). */
+    const int32_t* rebin_indptr;
+    const int32_t* rebin_index;
+    const double* rebin_weight;
 } SpammTemplateSet;
 
 /* Frozen snapshot of a Model after `model.data_spectrum = spectrum` and after
@@ -126,6 +134,14 @@ typedef struct SpammPlanDesc {
      * the kernel multiplies the flux summed so far by pow(10, -0.4 * E(B-V) * k), Model.py:384-395.
      * One parameter, E(B-V).  NULL unless a SPAMM_COMP_EXTINCTION is present. */
     const double* ext_k;
+
+    /* rebin_spec: True for BalmerCombined.log_conv (BalmerContinuumCombined.py:227,241): the two rebins
+     * around the (identity) convolution composed into one sparse P x P operator on the unnormalised
+     * continuum, CSR: bc_rebin_indptr [P + 1], bc_rebin_index, bc_rebin_weight.  All NULL: the two np.interp
+     * resamplings (the default), which the library collapses into a 4-tap stencil itself. */
+    const int32_t* bc_rebin_indptr;
+    const int32_t* bc_rebin_index;
+    const double* bc_rebin_weight;
 } SpammPlanDesc;
 
 typedef struct SpammPlan SpammPlan;
@@ -274,6 +290,13 @@ int spamm_stretch_run_sharded(SpammPlan* plan, SpammExchange* ex, double* walker
                               int32_t n_walkers, double a, uint64_t seed, uint64_t iter0, int32_t n_iter,
                               double* q_dev, double* z_dev, int64_t* naccepted_dev, double* chain_dev,
                               double* lnp_chain_dev, int64_t chain_len, void* stream);
+
+/* Timing probe of the template broadening kernels (FeComponent.py:285-319 / HostGalaxyComponent.py:292-325
+ * replaced by k_conv_rows + k_interp_rows + k_norm_rows) on their own: n_rows rows of family 0 (Fe) / 1 (host),
+ * every row with integer kernel width sigma_norm; mean durations over `repeats` launches (CUDA events) and the
+ * FMA count of one convolution launch.  Roofline evidence for the per-walker (DIRECT) broadening path. */
+int spamm_broadening_probe(SpammPlan* plan, int32_t family, int32_t sigma_norm, int32_t n_rows, int32_t repeats,
+                           double* conv_ms_out, double* interp_ms_out, double* conv_fma_out);
 
 /* FP64 FMA throughput probe (roofline denominator: MEASURED_PEAKS.json has no
  * FP64 entry).  Runs `iters` dependent-chain DFMA iterations on every SM and

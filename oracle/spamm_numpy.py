@@ -163,7 +163,7 @@ class OracleModel(object):
     """
 
     def __init__(self, wl, flux, err, comps=("PL", "FE", "HOST", "BC"), bc=True, bpc=True,
-                 broken_pl=False, line_type=None, templates=None, pars=None, ext_law=None):
+                 broken_pl=False, line_type=None, templates=None, pars=None, ext_law=None, rebin_spec=False):
         self.wl = np.asarray(wl, dtype=np.float64)
         self.flux = np.asarray(flux, dtype=np.float64)
         self.err = np.asarray(err, dtype=np.float64)
@@ -175,6 +175,9 @@ class OracleModel(object):
         self.tpl = templates if templates is not None else Templates()
         self.norm_wl = np.median(self.wl)                     # Spectrum.py:84-87
         self.ext_law = ext_law
+        # rebin_spec: True (parameters.yaml): every resampling goes through utils/rebin_spec.py, restated in
+        # extended precision by oracle/rebin_longdouble.py (parity unpinned, see there)
+        self.rebin_spec = bool(rebin_spec)
         # Extinction.extinction :188-205: no law selected => [1.] * P
         self.ext_k = extinction_k(self.wl, ext_law) if ext_law else np.zeros(len(self.wl))
         self._bounds = None
@@ -189,6 +192,8 @@ class OracleModel(object):
             lw = np.log(wl_t)
             x = np.linspace(min(lw), max(lw), num=len(wl_t))     # :173-175
             g = np.interp(x, lw, fx_t, left=0, right=0)          # :181-182
+            if self.rebin_spec:
+                g = self._rebin(lw, fx_t, x)                     # :184-186
             self.log_fe.append((x, g, np.median(wl_t)))          # median: :325
         self.log_host = []
         for wl_t, fx_t in self.tpl.host:
@@ -196,7 +201,14 @@ class OracleModel(object):
             lw = np.log(wl_t)
             x = np.linspace(min(lw), max(lw), num=len(wl_t))     # :173-175
             g = np.interp(x, lw, fx_t)                           # :179-181 (edge clamp)
+            if self.rebin_spec:
+                g = self._rebin(lw, fx_t, x)                     # :183-185
             self.log_host.append((x, g, np.median(wl_t)))        # median: :330
+
+    @staticmethod
+    def _rebin(wave, specin, wavnew):
+        from oracle.rebin_longdouble import rebin_spec_longdouble
+        return np.asarray(rebin_spec_longdouble(wave, specin, wavnew), dtype=np.float64)
 
     # -- parameter bookkeeping ----------------------------------------------
     def names(self):
@@ -355,7 +367,9 @@ class OracleModel(object):
             kernel = gaussian_window(sigma_size, sigma_norm) / \
                 (np.sqrt(2 * np.pi) * sigma_norm)                 # :292-293
             conv = np.convolve(g, kernel, mode="same")            # :304
-            if clamp_edges:
+            if self.rebin_spec:
+                f = self._rebin(x, conv, lnwl)                    # Fe:320-323 / HG:326-329
+            elif clamp_edges:
                 f = np.interp(lnwl, x, conv)                      # HG:323-325
             else:
                 f = np.interp(lnwl, x, conv, left=0, right=0)     # Fe:315-319
@@ -382,12 +396,16 @@ class OracleModel(object):
         ln_wavenew[0] = ln_wave[0]
         ln_wavenew[-1] = ln_wave[-1]
         flux_rebin = np.interp(ln_wavenew, ln_wave, orig_flux)
+        if self.rebin_spec:
+            flux_rebin = self._rebin(ln_wave, orig_flux, ln_wavenew)              # :227
         dpix = width_lines / (ln_wavenew[1] - ln_wavenew[0])
         kernel_width = round(5 * dpix)
         kernel_x = np.r_[-kernel_width:kernel_width + 1]
         kernel = np.exp(- (kernel_x) ** 2 / (dpix) ** 2)
         kernel /= abs(np.sum(kernel))
         flux_conv = np.convolve(flux_rebin, kernel, mode="same")
+        if self.rebin_spec:
+            return self._rebin(np.exp(ln_wavenew), flux_conv, self.wl)            # :241
         return np.interp(self.wl, np.exp(ln_wavenew), flux_conv)
 
     def bc_flux(self, p):

@@ -69,10 +69,37 @@ class Model(object):
             raise Exception("Components must be added before defining the data spectrum.")
         self.model_spectrum.spectral_axis = np.array(new_data_spectrum.spectral_axis)
         self.model_spectrum.flux = np.zeros(len(self.model_spectrum.spectral_axis))
+        # Components coarser than the data (Model.py:196-240).  The shipped components report no grid
+        # spacing (App. B Q9: the template components' `is_analytic` is a method, so `grid_spacing()` is
+        # None), hence the model grid is the data grid; a plugin component that does report a spacing
+        # coarser than the data takes the branches below.
+        gs = 0
+        worst_component = None
         for component in self.components:
             component.initialize(data_spectrum=new_data_spectrum)
-        # template components report no grid spacing (App. B Q9), so the model grid
-        # is always the data grid and no resampling branch exists here
+            if component.grid_spacing() and component.grid_spacing() > gs:
+                gs = component.grid_spacing()
+                worst_component = component
+        self.worst_component = worst_component
+        if gs > new_data_spectrum.grid_spacing():
+            if self.upsample_components_if_needed:
+                pass            # components are evaluated on the data grid anyway
+            elif self.downsample_data_if_needed:
+                # The data are resampled onto the coarsest component's spacing and everything -- model grid,
+                # components, likelihood -- moves to that grid.  (The reference's lines 219-231 index the
+                # Spectrum object and store an unevaluated interp1d, so they raise; this is what they set
+                # out to do, with the errors resampled linearly like the flux.)
+                wl = np.asarray(new_data_spectrum.spectral_axis, dtype=np.float64)
+                new_wl = np.arange(wl[0], wl[-1], gs)
+                downsampled = Spectrum(spectral_axis=new_wl,
+                                       flux=np.interp(new_wl, wl, np.asarray(new_data_spectrum.flux)),
+                                       flux_error=np.interp(new_wl, wl, np.asarray(new_data_spectrum.flux_error)))
+                self._data_spectrum = downsampled
+                self.model_spectrum.spectral_axis = np.array(new_wl)
+                self.model_spectrum.flux = np.zeros(len(new_wl))
+                for component in self.components:
+                    component.initialize(data_spectrum=downsampled)
+            # else: the reference's `assert True, "... courser wavelength grid spacing ..."` never fires
         self._plan = None
 
     # -- plan ------------------------------------------------------------------------

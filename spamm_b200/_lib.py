@@ -9,7 +9,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPAMM_B200_LIB", os.path.join(PKG, "libspamm_b200.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_COMPONENTS = 8
 MAX_TEMPLATES = 16
 SH95_NE, SH95_T, SH95_LINES = 7, 10, 48
@@ -33,6 +33,9 @@ class SpammTemplateSet(ctypes.Structure):
         ("sqrt_2pi", ctypes.c_double),
         ("kernel_size_sigma", ctypes.c_int32),
         ("clamp_edges", ctypes.c_int32),
+        ("rebin_indptr", ctypes.POINTER(ctypes.c_int32)),
+        ("rebin_index", ctypes.POINTER(ctypes.c_int32)),
+        ("rebin_weight", c_double_p),
     ]
 
 
@@ -76,6 +79,9 @@ class SpammPlanDesc(ctypes.Structure):
         ("balmer_edge", ctypes.c_double),
         ("max_walkers", ctypes.c_int32),
         ("ext_k", c_double_p),
+        ("bc_rebin_indptr", ctypes.POINTER(ctypes.c_int32)),
+        ("bc_rebin_index", ctypes.POINTER(ctypes.c_int32)),
+        ("bc_rebin_weight", c_double_p),
     ]
 
 
@@ -85,7 +91,7 @@ EXPORTS = [
     "spamm_model_flux_batch", "spamm_likelihood_batch", "spamm_plan_n_dim", "spamm_plan_n_pix", "spamm_plan_template_mode",
     "spamm_plan_bank_rows", "spamm_plan_status", "spamm_plan_launch_count", "spamm_plan_set_walker_split", "spamm_plan_specialised",
     "spamm_stretch_propose", "spamm_stretch_accept", "spamm_chain_record", "spamm_stretch_run",
-    "spamm_fp64_peak_probe", "spamm_last_error", "spamm_abi_version", "spamm_plan_check",
+    "spamm_fp64_peak_probe", "spamm_broadening_probe", "spamm_last_error", "spamm_abi_version", "spamm_plan_check",
     "spamm_shard_bounds", "spamm_exchange_region_bytes", "spamm_exchange_create", "spamm_exchange_connect",
     "spamm_exchange_connect_ptrs", "spamm_exchange_region_ptr", "spamm_exchange_epoch", "spamm_exchange_destroy",
     "spamm_lnpost_batch_sharded", "spamm_lnpost_batch_sharded_host", "spamm_stretch_run_sharded",
@@ -176,6 +182,9 @@ def load():
     lib.spamm_lnpost_batch_sharded_host.restype = ctypes.c_int
     lib.spamm_stretch_run_sharded.argtypes = [vp, vp, vp, vp, i32, dbl, u64, u64, i32, vp, vp, vp, vp, vp, i64, vp]
     lib.spamm_stretch_run_sharded.restype = ctypes.c_int
+    lib.spamm_broadening_probe.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl),
+                                           ctypes.POINTER(dbl)]
+    lib.spamm_broadening_probe.restype = ctypes.c_int
     lib.spamm_fp64_peak_probe.argtypes = [i32, i32, ctypes.POINTER(dbl)]
     lib.spamm_fp64_peak_probe.restype = ctypes.c_int
     lib.spamm_last_error.argtypes = []
@@ -192,6 +201,12 @@ def check(rc):
     if rc != 0:
         msg = load().spamm_last_error()
         raise SpammError("spamm_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def as_c_i32(arr):
+    """int32 C-contiguous copy + its int32_t* (keep the array alive!)."""
+    a = np.ascontiguousarray(arr, dtype=np.int32)
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
 
 
 def as_c(arr):

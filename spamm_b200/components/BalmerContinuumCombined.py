@@ -122,6 +122,18 @@ class BalmerCombined(Component):
         b, bp = _lib.as_c(np.exp(ln_wavenew))
         desc.bc_ln_wl_new, desc.bc_exp_ln_wl_new = ap, bp
         keep += [a, b]
+        if self.BC and not self.fast_interp:
+            # rebin_spec: True (BC:227,241): both resamplings of log_conv are flux-conserving rebins; with the
+            # identity kernel between them (App. B: c in cm/s) they compose into one sparse operator on f0
+            from ..utils.rebin_spec import rebin_matrix, compose_csr
+            to_log = rebin_matrix(ln_wave, ln_wavenew)
+            back = rebin_matrix(np.exp(ln_wavenew), wl)
+            ip, ix, w = compose_csr(back, to_log, len(wl))
+            ipc, ipp = _lib.as_c_i32(ip)
+            ixc, ixp = _lib.as_c_i32(ix)
+            wc, wp = _lib.as_c(w)
+            keep += [ipc, ixc, wc]
+            desc.bc_rebin_indptr, desc.bc_rebin_index, desc.bc_rebin_weight = ipp, ixp, wp
         desc.c_kms, desc.c_cgs, desc.c_aa = constants.C_KMS, constants.C_CGS, constants.C_AA
         desc.h_cgs, desc.kb_cgs = constants.H_CGS, constants.KB_CGS
         desc.balmer_edge = float(balmer_edge)

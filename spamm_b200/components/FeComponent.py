@@ -72,5 +72,7 @@ class FeComponent(TemplateComponent):
     def plan_fill(self, desc, keep, spectrum):
         if self.log_fe is None:
             self.initialize(spectrum)
-        desc.fe = self._template_set(self.fe_templ, self.log_fe, self.templ_width,
-                                     self.inputpars["fe_kernel_size_sigma"], keep)
+        ts = self._template_set(self.fe_templ, self.log_fe, self.templ_width,
+                                self.inputpars["fe_kernel_size_sigma"], keep)
+        self._rebin_operators(ts, self.log_fe, spectrum, keep)
+        desc.fe = ts

@@ -73,5 +73,7 @@ class HostGalaxyComponent(TemplateComponent):
     def plan_fill(self, desc, keep, spectrum):
         if self.log_host is None:
             self.initialize(spectrum)
-        desc.host = self._template_set(self.host_gal, self.log_host, self.templ_stellar_disp,
-                                       self.inputpars["hg_kernel_size_sigma"], keep)
+        ts = self._template_set(self.host_gal, self.log_host, self.templ_stellar_disp,
+                                self.inputpars["hg_kernel_size_sigma"], keep)
+        self._rebin_operators(ts, self.log_host, spectrum, keep)
+        desc.host = ts

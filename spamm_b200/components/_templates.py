@@ -38,9 +38,10 @@ class TemplateComponent(Component):
             ln = np.log(template.spectral_axis)
             log_wl = np.linspace(min(ln), max(ln), num=len(template.spectral_axis))
             if not self.fast_interp:
-                raise NotImplementedError("rebin_spec: True (pysynphot flux-conserving rebin) "
-                                          "is not part of the GPU path")
-            if self._clamp_edges:
+                # rebin_spec: True (Fe:184-186 / HG:183-185): flux-conserving rebin, utils/rebin_spec.py
+                from ..utils.rebin_spec import rebin_spec
+                log_flux = rebin_spec(ln, template.flux, log_wl)
+            elif self._clamp_edges:
                 log_flux = np.interp(log_wl, ln, template.flux)
             else:
                 log_flux = np.interp(log_wl, ln, template.flux, left=0, right=0)
@@ -72,3 +73,23 @@ class TemplateComponent(Component):
         ts.kernel_size_sigma = int(ksize)
         ts.clamp_edges = 1 if self._clamp_edges else 0
         return ts
+
+    def _rebin_operators(self, ts, log_templates, spectrum, keep):
+        """rebin_spec: True -- the per-call rebin of the convolved row onto ln(data wavelengths)
+        (Fe:320-323 / HG:326-329) as one CSR matrix per template, applied on the device."""
+        if self.fast_interp:
+            return
+        from ..utils.rebin_spec import rebin_matrix
+        ln_data = np.log(np.asarray(spectrum.spectral_axis, dtype=np.float64))
+        ptrs, idxs, ws, base = [], [], [], 0
+        for lt in log_templates:
+            ip, ix, w = rebin_matrix(np.asarray(lt.spectral_axis, dtype=np.float64), ln_data)
+            ptrs.append(ip + base)
+            idxs.append(ix)
+            ws.append(w)
+            base += len(ix)
+        ip, ipp = _lib.as_c_i32(np.concatenate(ptrs))
+        ix, ixp = _lib.as_c_i32(np.concatenate(idxs))
+        w, wp = _lib.as_c(np.concatenate(ws))
+        keep += [ip, ix, w]
+        ts.rebin_indptr, ts.rebin_index, ts.rebin_weight = ipp, ixp, wp

@@ -19,7 +19,10 @@ constexpr int kThreads = SPAMM_THREADS;  // threads per CTA of the fused kernel
 constexpr int kPix = SPAMM_PIX;        // pixels per lane in the line loop
 constexpr int kMaxDim = 64;            // max parameters per walker
 constexpr int kMaxLines = 1024;
-constexpr int kConvTile = 256;
+constexpr int kConvR = 8, kConvThreads = 128;          // broadening kernel: outputs per thread, threads per CTA
+constexpr int kConvTile = kConvR * kConvThreads;       // output points per CTA
+// words per residue class of the transposed template tile (tile + halo of Mp - 1 points, Mp = padded taps)
+__host__ __device__ inline int conv_group_stride(int Mp) { return (kConvTile + Mp - 1 + kConvR - 1) / kConvR + 1; }
 
 enum StatusBits : int {
     kStatSigmaRange = 1,   // sigma_norm outside the bank / < 1
@@ -52,6 +55,11 @@ struct TemplDev {
     const double* logf;
     const double* bank_f;                 // [rows][P]
     const double* bank_nf;                // [rows]
+    // rebin_spec: True -- the flux-conserving rebin onto the data grid as a CSR matrix per template
+    // (rb_ptr [n_templ][P + 1], template-local columns); null: np.interp
+    const int* rb_ptr;
+    const int* rb_idx;
+    const double* rb_w;
 };
 
 struct PlanDev {
@@ -88,6 +96,10 @@ struct PlanDev {
     double mom_Sref;
     int mom_poly;
     const double *bc_hnu, *bc_K, *bc_t3;
+    // rebin_spec: True -- log_conv's two rebins composed into one sparse operator on f0 (CSR); null: the stencil
+    const int* bc_rb_ptr;
+    const int* bc_rb_idx;
+    const double* bc_rb_w;
     const int4* bc_idx;                   // 4 source pixels of the log_conv stencil
     const double *bc_tb0, *bc_tb1, *bc_ta;
     int edge_guess;                       // insertion point of balmer_edge in wl

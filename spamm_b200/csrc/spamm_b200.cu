@@ -72,7 +72,9 @@ struct SpammPlan {
     double *h_params = nullptr, *h_lnp = nullptr, *d_params = nullptr, *d_lnp = nullptr;
     cudaStream_t own_stream = nullptr;
     int max_sigma_seen = 0;
+    int sig_cap_fe = 0, sig_cap_host = 0;   // widest sigma_norm the width priors admit (0: no bounded prior)
     int last_bank_rows = 0;
+    int last_sig_cap = 0;
     int split_mode = 1;          // 0: never split a walker; 1: auto; 2/4/8: forced cluster size; 3: forced two-part split
     int* h_status = nullptr;           // pinned copy of the device status word (mapped; see deferred_status)
     double* d_part_chi = nullptr;      // walker parts: per-chunk chi^2 partials [max_walkers][n_chunks]
@@ -107,8 +109,8 @@ static int dalloc(SpammPlan* pl, size_t n, T** dev_out) {
 }
 
 static int conv_smem_bytes(int ksize, int max_sigma) {
-    int M = ksize * max_sigma;
-    return (M + kConvTile + M - 1) * (int)sizeof(double);
+    const int Mp = (ksize * max_sigma + kConvR - 1) & ~(kConvR - 1);
+    return (Mp + kConvR * conv_group_stride(Mp)) * (int)sizeof(double);
 }
 
 // run the broadening pipeline for n_rows rows -> frows[n_rows][P], nf[n_rows]
@@ -124,7 +126,7 @@ static int run_rows(SpammPlan* pl, const TemplDev& ts, const int* d_row_t, const
     int nmax = 0;
     for (int t = 0; t < ts.n_templ; ++t) nmax = std::max(nmax, ts.n_pts[t]);
     dim3 g1((nmax + kConvTile - 1) / kConvTile, n_rows);
-    k_conv_rows<<<g1, kConvTile, smem, st>>>(ts, d_row_t, d_row_sig, d_conv, stride);
+    k_conv_rows<<<g1, kConvThreads, smem, st>>>(ts, d_row_t, d_row_sig, d_conv, stride);
     dim3 g2((pl->dev.P + 255) / 256, n_rows);
     k_interp_rows<<<g2, 256, 0, st>>>(ts, d_row_t, d_conv, stride, pl->dev.lnwl, pl->dev.P, d_frows);
     k_norm_rows<<<(n_rows + 127) / 128, 128, 0, st>>>(ts, d_row_t, n_rows, pl->dev.wl, pl->dev.P,
@@ -167,8 +169,35 @@ static int setup_template_set(SpammPlan* pl, const SpammTemplateSet& src, int pa
     if ((rc = upload(pl, src.log_wl, total, &ts.logx))) return rc;
     if ((rc = upload(pl, src.log_flux, total, &ts.logf))) return rc;
     for (int t = 0; t < ts.n_templ; ++t) pl->conv_stride = std::max(pl->conv_stride, ts.n_pts[t]);
+    ts.rb_ptr = nullptr; ts.rb_idx = nullptr; ts.rb_w = nullptr;
+    if (src.rebin_indptr && src.rebin_index && src.rebin_weight) {
+        const size_t np1 = (size_t)ts.n_templ * (pl->dev.P + 1);
+        const int nnz = src.rebin_indptr[np1 - 1];
+        for (int t = 0; t < ts.n_templ; ++t) {
+            const int32_t* ptr = src.rebin_indptr + (size_t)t * (pl->dev.P + 1);
+            for (int i = 0; i < pl->dev.P; ++i) {
+                if (ptr[i + 1] < ptr[i] || ptr[i + 1] > nnz) return set_error(SPAMM_EINVAL, "rebin operator: bad row pointers");
+                for (int k = ptr[i]; k < ptr[i + 1]; ++k)
+                    if (src.rebin_index[k] < 0 || src.rebin_index[k] >= ts.n_pts[t])
+                        return set_error(SPAMM_EINVAL, "rebin operator: column outside the template");
+            }
+        }
+        if ((rc = upload(pl, src.rebin_indptr, np1, &ts.rb_ptr))) return rc;
+        if ((rc = upload(pl, src.rebin_index, (size_t)nnz, &ts.rb_idx))) return rc;
+        if ((rc = upload(pl, src.rebin_weight, (size_t)nnz, &ts.rb_w))) return rc;
+    }
 
     *bank_ok = false;
+    pl->last_sig_cap = 0;
+    if (std::isfinite(width_hi)) {
+        int cap = 0;
+        for (int t = 0; t < ts.n_templ; ++t) {
+            double sn = host_sigma_norm(src, ts.bin[t], width_hi);
+            if (!(sn >= 1.0) || sn > 1.0e6) { cap = 0; break; }
+            cap = std::max(cap, (int)sn);
+        }
+        pl->last_sig_cap = cap;
+    }
     if (want_bank && std::isfinite(width_hi)) {
         int rows = 0;
         bool ok = true;
@@ -325,6 +354,7 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         double hi = d->prior_hi ? d->prior_hi[off_fe + d->fe.n_templates] : INFINITY;
         if ((rc = setup_template_set(pl, d->fe, off_fe, hi, want_bank, &pd.fe, &ok))) return rc;
         pd.fe_rows = ok ? pl->last_bank_rows : 0;
+        pl->sig_cap_fe = pl->last_sig_cap;
         all_bank = all_bank && ok;
     }
     if (seen[SPAMM_COMP_HOST]) {
@@ -332,6 +362,7 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
         double hi = d->prior_hi ? d->prior_hi[off_host + d->host.n_templates] : INFINITY;
         if ((rc = setup_template_set(pl, d->host, off_host, hi, want_bank, &pd.host, &ok))) return rc;
         pd.host_rows = ok ? pl->last_bank_rows : 0;
+        pl->sig_cap_host = pl->last_sig_cap;
         all_bank = all_bank && ok;
     }
     if (d->template_mode == SPAMM_TEMPLATES_BANK && !all_bank)
@@ -501,6 +532,24 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
             if ((rc = upload(pl, tb0.data(), P, &pd.bc_tb0))) return rc;
             if ((rc = upload(pl, tb1.data(), P, &pd.bc_tb1))) return rc;
             if ((rc = upload(pl, ta.data(), P, &pd.bc_ta))) return rc;
+            pd.bc_rb_ptr = nullptr; pd.bc_rb_idx = nullptr; pd.bc_rb_w = nullptr;
+            const bool bc_rebin = d->bc_rebin_indptr && d->bc_rebin_index && d->bc_rebin_weight;
+            if (bc_rebin) {
+                const int nnz = d->bc_rebin_indptr[P];
+                for (int i = 0; i < P; ++i) {
+                    if (d->bc_rebin_indptr[i + 1] < d->bc_rebin_indptr[i] || d->bc_rebin_indptr[i + 1] > nnz)
+                        return set_error(SPAMM_EINVAL, "log_conv rebin operator: bad row pointers");
+                    for (int k = d->bc_rebin_indptr[i]; k < d->bc_rebin_indptr[i + 1]; ++k) {
+                        if (d->bc_rebin_index[k] < 0 || d->bc_rebin_index[k] >= P)
+                            return set_error(SPAMM_EINVAL, "log_conv rebin operator: column outside the grid");
+                        if (k > d->bc_rebin_indptr[i] && d->bc_rebin_index[k] <= d->bc_rebin_index[k - 1])
+                            return set_error(SPAMM_EINVAL, "log_conv rebin operator: columns must ascend within a row");
+                    }
+                }
+                if ((rc = upload(pl, d->bc_rebin_indptr, (size_t)P + 1, &pd.bc_rb_ptr))) return rc;
+                if ((rc = upload(pl, d->bc_rebin_index, (size_t)nnz, &pd.bc_rb_idx))) return rc;
+                if ((rc = upload(pl, d->bc_rebin_weight, (size_t)nnz, &pd.bc_rb_w))) return rc;
+            }
             // stage f0 up to the furthest source pixel of (nearest pixel to the edge) + 2
             int ibe = 0;
             double best = INFINITY;
@@ -509,7 +558,11 @@ static int plan_create_impl(const SpammPlanDesc* d, SpammPlan* pl) {
                 if (v < best) { best = v; ibe = i; }
             }
             int itop = std::min(ibe + 2, P - 1), top = 0;
-            for (int i = 0; i <= itop; ++i) top = std::max(top, std::max(idx[i].y, idx[i].w));
+            for (int i = 0; i <= itop; ++i) {
+                top = std::max(top, std::max(idx[i].y, idx[i].w));
+                if (bc_rebin && d->bc_rebin_indptr[i + 1] > d->bc_rebin_indptr[i])
+                    top = std::max(top, (int)d->bc_rebin_index[d->bc_rebin_indptr[i + 1] - 1]);
+            }
             pd.bc_nstage = std::min(P, top + 1);
         }
         // insertion point of the Balmer edge: start of the per-walker edge-pixel search
@@ -712,14 +765,17 @@ static int ensure_direct_ws(SpammPlan* pl) {
     return SPAMM_OK;
 }
 
+// sig_cap > 0: ln-posterior path with a bounded width prior -- the shared-memory stage is sized for the prior's
+// widest kernel and nothing is read back (the call stays asynchronous); 0: flux() with arbitrary widths
 static int direct_rows_for_chunk(SpammPlan* pl, const TemplDev& ts, const double* params_dev, int w0,
-                                 int nW, double* d_f, double* d_nf, cudaStream_t st) {
+                                 int nW, double* d_f, double* d_nf, cudaStream_t st, int sig_cap) {
     int n_rows = nW * ts.n_templ;
     k_rows_from_params<<<(n_rows + 127) / 128, 128, 0, st>>>(ts, params_dev, pl->dev.D, w0, nW,
-                                                               pl->d_row_t, pl->d_row_sig);
+                                                               pl->d_row_t, pl->d_row_sig, sig_cap);
     pl->launches += 1;
-    // the widest kernel decides the shared-memory size: read the sigmas back (direct mode is the
-    // cross-check path, not the throughput path)
+    if (sig_cap > 0)
+        return run_rows(pl, ts, pl->d_row_t, pl->d_row_sig, n_rows, sig_cap, pl->d_conv, pl->conv_stride, d_f, d_nf, st);
+    // the widest kernel decides the shared-memory size: read the sigmas back (synchronises the stream)
     std::vector<int> sig(n_rows);
     CUDA_TRY(cudaMemcpyAsync(sig.data(), pl->d_row_sig, n_rows * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -789,6 +845,7 @@ static bool parts_for(const SpammPlan* pl, const PlanDev& pd, int n_walkers) {
 static int spec_of(const SpammPlan* pl, const PlanDev& pd, uint32_t mask, const DirectRows& dr) {
     if (!pl->use_full_kernel || mask != (1u << pd.n_comp) - 1u || dr.fe_f || dr.host_f) return 0;
     if (!pd.exp_safe || !pd.nc_pair_ok || pd.lo == nullptr || pd.nc_broken) return 0;
+    if (pd.bc_rb_ptr != nullptr) return 0;            // rebin_spec: True runs the generic instantiation
     int spec = 0, last = -1;
     for (int q = 0; q < pd.n_comp; ++q) {
         const int kind = pd.comp_kind[q];
@@ -875,11 +932,13 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
         int nW = std::min(pl->direct_chunk, n_walkers - w0);
         DirectRows dr{nullptr, nullptr, nullptr, nullptr};
         if (need_fe) {
-            if ((rc = direct_rows_for_chunk(pl, pd.fe, params_dev, w0, nW, pl->d_fe_f, pl->d_fe_nf, st))) return rc;
+            if ((rc = direct_rows_for_chunk(pl, pd.fe, params_dev, w0, nW, pl->d_fe_f, pl->d_fe_nf, st,
+                                            MODE == 0 && pd.lo ? pl->sig_cap_fe : 0))) return rc;
             dr.fe_f = pl->d_fe_f; dr.fe_nf = pl->d_fe_nf;
         }
         if (need_host) {
-            if ((rc = direct_rows_for_chunk(pl, pd.host, params_dev, w0, nW, pl->d_host_f, pl->d_host_nf, st))) return rc;
+            if ((rc = direct_rows_for_chunk(pl, pd.host, params_dev, w0, nW, pl->d_host_f, pl->d_host_nf, st,
+                                            MODE == 0 && pd.lo ? pl->sig_cap_host : 0))) return rc;
             dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
         }
         double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
@@ -1320,6 +1379,69 @@ extern "C" int spamm_debug_set_trace(unsigned long long* buf) {
     return SPAMM_OK;
 }
 #endif
+
+// Timing probe of the broadening kernels on their own (roofline evidence for the per-walker DIRECT path):
+// n_rows rows of family 0 (Fe) / 1 (host), templates cycled, every row with kernel width sigma_norm, run
+// `repeats` times; returns the mean duration of k_conv_rows and of k_interp_rows + k_norm_rows (CUDA events)
+// and the FMA count of one k_conv_rows launch (N_t * M per row: the SURVEY 8(d) convolution term / 2).
+extern "C" int spamm_broadening_probe(SpammPlan* pl, int32_t family, int32_t sigma_norm, int32_t n_rows,
+                                      int32_t repeats, double* conv_ms_out, double* interp_ms_out,
+                                      double* conv_fma_out) {
+    if (!pl || n_rows < 1 || repeats < 1 || sigma_norm < 1) return set_error(SPAMM_EINVAL, "bad argument");
+    const TemplDev& ts = family == 0 ? pl->dev.fe : pl->dev.host;
+    if (ts.n_templ < 1 || !ts.logf) return set_error(SPAMM_EINVAL, "plan has no such template family");
+    std::vector<int> rt(n_rows), rs(n_rows, sigma_norm);
+    int stride = 0;
+    double fma_count = 0.0;
+    for (int t = 0; t < ts.n_templ; ++t) stride = std::max(stride, ts.n_pts[t]);
+    for (int r = 0; r < n_rows; ++r) {
+        rt[r] = r % ts.n_templ;
+        fma_count += (double)ts.n_pts[rt[r]] * ts.ksize * sigma_norm;
+    }
+    int *d_rt = nullptr, *d_rs = nullptr;
+    double *d_conv = nullptr, *d_f = nullptr, *d_nf = nullptr;
+    CUDA_TRY(cudaMalloc(&d_rt, n_rows * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_rs, n_rows * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_conv, (size_t)n_rows * stride * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_f, ((size_t)n_rows * pl->dev.P + kPad) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_nf, (size_t)n_rows * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(d_rt, rt.data(), n_rows * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_rs, rs.data(), n_rows * sizeof(int), cudaMemcpyHostToDevice));
+    const int smem = conv_smem_bytes(ts.ksize, sigma_norm);
+    int rc = SPAMM_OK;
+    if (smem > 200 * 1024) rc = set_error(SPAMM_ERANGE, "broadening kernel too wide for shared memory");
+    if (!rc && smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_conv_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        rc = set_error(SPAMM_ECUDA, "cudaFuncSetAttribute(k_conv_rows)");
+    if (!rc) {
+        int nmax = stride;
+        dim3 g1((nmax + kConvTile - 1) / kConvTile, n_rows), g2((pl->dev.P + 255) / 256, n_rows);
+        cudaEvent_t e0, e1, e2;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        double tc = 0.0, ti = 0.0;
+        for (int it = 0; it <= repeats; ++it) {          // iteration 0 warms up
+            cudaEventRecord(e0);
+            k_conv_rows<<<g1, kConvThreads, smem>>>(ts, d_rt, d_rs, d_conv, stride);
+            cudaEventRecord(e1);
+            k_interp_rows<<<g2, 256>>>(ts, d_rt, d_conv, stride, pl->dev.lnwl, pl->dev.P, d_f);
+            k_norm_rows<<<(n_rows + 127) / 128, 128>>>(ts, d_rt, n_rows, pl->dev.wl, pl->dev.P, d_f, d_nf);
+            cudaEventRecord(e2);
+            cudaEventSynchronize(e2);
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e0, e1);
+            cudaEventElapsedTime(&b, e1, e2);
+            if (it) { tc += a; ti += b; }
+        }
+        pl->launches += 3 * (repeats + 1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(SPAMM_ECUDA, "broadening probe launch failed");
+        if (conv_ms_out) *conv_ms_out = tc / repeats;
+        if (interp_ms_out) *interp_ms_out = ti / repeats;
+        if (conv_fma_out) *conv_fma_out = fma_count;
+    }
+    cudaFree(d_rt); cudaFree(d_rs); cudaFree(d_conv); cudaFree(d_f); cudaFree(d_nf);
+    return rc;
+}
 
 extern "C" int spamm_fp64_peak_probe(int32_t iters, int32_t repeats, double* tflops_out) {
     if (!tflops_out || iters < 1 || repeats < 1) return set_error(SPAMM_EINVAL, "bad argument");

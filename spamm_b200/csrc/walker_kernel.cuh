@@ -202,7 +202,14 @@ __device__ __forceinline__ void bc_f0_pair(double2 hnu, double2 K, double2 t3, d
 // log_conv output at data pixel i (BC:225-239 with kernel == [1.0]): the two np.interp
 // resamplings collapse to a 4-tap stencil on f0 with walker-independent weights
 //   fr_j = f0[k] + (f0[k+1]-f0[k]) tB_j ;  out_i = fr_j + (fr_{j+1}-fr_j) tA_i
+// (rebin_spec: True, generic instantiation only: the composed rebin operator's row i instead)
+template <bool FULL = false>
 __device__ __forceinline__ double bc_conv_at(const PlanDev& pl, const double* __restrict__ f0s, int i) {
+    if (!FULL && pl.bc_rb_ptr != nullptr) {
+        double acc = 0.0;
+        for (int k = pl.bc_rb_ptr[i]; k < pl.bc_rb_ptr[i + 1]; ++k) acc += pl.bc_rb_w[k] * f0s[pl.bc_rb_idx[k]];
+        return acc;
+    }
     const int4 kk = pl.bc_idx[i];              // k0, k0', k1, k1'
     const double tb0 = pl.bc_tb0[i], tb1 = pl.bc_tb1[i], ta = pl.bc_ta[i];
     double a0 = f0s[kk.x], a1 = f0s[kk.z];
@@ -651,8 +658,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double dpix = (b_lwid / pl.c_cgs) / pl.bc_dlnew;
             if (rint(5 * dpix) != 0.0) flag_status(pl.status, pl.status_host, kStatBcKernel);
             const int4 kk = pl.bc_idx[is];
+            int top = max(kk.y, kk.w);
+            if (!FULL && pl.bc_rb_ptr != nullptr) top = pl.bc_rb_idx[pl.bc_rb_ptr[is + 1] - 1];   // columns ascend
             // (reported as an error by the host; no Balmer-continuum pixel is evaluated so nothing reads past the stage)
-            if (max(kk.y, kk.w) >= pl.bc_nstage) { flag_status(pl.status, pl.status_host, kStatBcStage); c.bc_istar = -1; }
+            if (top >= pl.bc_nstage) { flag_status(pl.status, pl.status_host, kStatBcStage); c.bc_istar = -1; }
         }
     }
     if (warp == 4 % kNW && lane == 0) {
@@ -733,7 +742,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     const int bc_istar = c.bc_istar, bpc_istar = c.bpc_istar;
     double bpc_scale = 0.0;
     if (do_bc && warp == kNW - 1 && lane == 0) {
-        double fnorm = bc_istar >= 0 ? bc_conv_at(pl, sF0, bc_istar) : CUDART_NAN;     // BC:444
+        double fnorm = bc_istar >= 0 ? bc_conv_at<FULL>(pl, sF0, bc_istar) : CUDART_NAN;     // BC:444
         c.bc_scale = b_norm / fnorm;                                     // BC:446
         c.bc_finite = isfinite(c.bc_scale) ? 1 : 0;
     }
@@ -1043,7 +1052,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             double v = m[q];
             if (have_balmer) {
                 double bc = 0.0, bpc = 0.0;
-                if (task_bc) bc = ((i <= bc_istar) ? bc_conv_at(pl, sF0, i) : 0.0) * bc_scale; // BC:445-446
+                if (task_bc) bc = ((i <= bc_istar) ? bc_conv_at<FULL>(pl, sF0, i) : 0.0) * bc_scale; // BC:445-446
                 if (do_bpc) bpc = ((i > bpc_istar) ? acc[q] : 0.0) * bpc_scale;                // BC:386-387
                 v = v + ((do_bc && do_bpc) ? bc + bpc : (do_bc ? bc : bpc));                   // BC:462-471
             }
