@@ -500,7 +500,11 @@ def run_ours(args):
             torch.cuda.synchronize()
             res[name] = float(np.mean([e0.elapsed_time(e1) for e0, e1 in evb]))
             res[name + "_values"] = ob.cpu().numpy().copy()
-        assert np.array_equal(res["bank_values"], res["direct_values"]), "bank and direct broadening disagree"
+        # (the bank runs the NC+Fe specialised instantiation of the walker kernel, per-walker rows the generic one:
+        #  same rows bit for bit -- tests/test_gpu_parity.py::test_bank_equals_direct_broadening -- a few ulp apart
+        #  in the final sum)
+        bd_rel = float(np.max(np.abs(res["bank_values"] - res["direct_values"]) / np.abs(res["bank_values"])))
+        assert bd_rel < 1e-12, "bank and direct broadening disagree"
         hbm = 6465.2
         mp_ = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(mp_):
@@ -521,7 +525,7 @@ def run_ours(args):
             "config2": {"workload": "NC + Fe, 1024 walkers x 4096 px (BASELINE config 2)",
                         "bank_ms": res["bank"], "direct_ms": res["direct"],
                         "direct_evals_per_s": 1024 / (res["direct"] * 1e-3),
-                        "bit_identical": True,
+                        "max_rel_diff_bank_vs_direct": bd_rel,
                         "what": "direct = k_rows_from_params + k_conv_rows + k_interp_rows + k_norm_rows per call "
                                 "(3072 rows), then k_walkers; asynchronous (kernel widths bounded by the width prior)"},
             "kernels": probes,

@@ -110,7 +110,7 @@ __global__ void k_interp_rows(TemplDev ts, const int* __restrict__ row_t,
     }
     double left = ts.clamp ? fp[0] : 0.0;
     double right = ts.clamp ? fp[N - 1] : 0.0;
-    frows[(size_t)r * P + i] = np_interp_at(lnwl[i], xp, fp, N, left, right);
+    frows[(size_t)r * P + i] = np_interp_at<true>(lnwl[i], xp, fp, N, left, right);
 }
 
 // nf = np.nan_to_num(np.interp(median(template wl), wl, f))     Fe:325-331 / HG:330-336
