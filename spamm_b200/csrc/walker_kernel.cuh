@@ -72,11 +72,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// raise this rank's flag in every rank's flag block
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// raise this rank's flag in every rank's flag block: ONE system-scope fence orders every result of the call
+// before the flag stores, which then go out back to back (a release store per peer would wait for the NVLink
+// round trip of the one before it: measured +8 us per call on 8 GPUs)
 __device__ __forceinline__ void raise_flags(const PeerOut& po) {
     __threadfence_system();
     for (int r = 0; r < po.n_peers; ++r)
-        st_release_sys(reinterpret_cast<unsigned long long*>(po.bufs[r]) + po.rank, po.epoch);
+        st_relaxed_sys(reinterpret_cast<unsigned long long*>(po.bufs[r]) + po.rank, po.epoch);
 }
 
 __device__ __forceinline__ void store_result(double* out, int w, double v, const PeerOut& po) {
