@@ -1138,6 +1138,7 @@ struct SpammExchange {
     unsigned long long* d_peer_ptrs = nullptr;   // device copy of `peer`
     unsigned* d_done = nullptr;            // retired-walker counter of the running call
     bool connected = false;
+    bool pdl = getenv("SPAMM_EXCHANGE_PDL") ? atoi(getenv("SPAMM_EXCHANGE_PDL")) != 0 : true;
     // staging of the *_host entry point
     double *h_params = nullptr, *h_lnp = nullptr, *d_params = nullptr;
     cudaStream_t own_stream = nullptr;
@@ -1274,10 +1275,19 @@ static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_d
 // wait for every rank's flag and pull the other ranks' slices into this rank's region (and into `copy`)
 static int queue_gather(SpammPlan* pl, SpammExchange* ex, const PeerIn& pi, int32_t n_total, double* copy,
                         cudaStream_t st) {
-    k_gather<<<(n_total + 255) / 256, 256, 0, st>>>(pi, n_total, copy);
+    // programmatic stream serialisation: the gather kernel may start while the walker kernel before it drains
+    // (it synchronises through the exchange flags, never through the grid dependency)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n_total + 255) / 256), 1, 1);
+    cfg.blockDim = dim3(256, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = ex->pdl ? 1 : 0;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_gather, pi, n_total, copy));
     pl->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    (void)ex;
     return SPAMM_OK;
 }
 
@@ -1359,10 +1369,18 @@ extern "C" int spamm_stretch_run_sharded(SpammPlan* pl, SpammExchange* ex, doubl
             if (rc) return rc;
             PeerIn pi;
             if ((rc = sharded_eval(pl, ex, q_dev, Ns, st, &pi))) return rc;
-            k_stretch_accept<<<(Ns + 127) / 128, 128, 0, st>>>(
-                walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, nullptr, seed, iteration,
-                reinterpret_cast<long long*>(naccepted_dev), pi);
-            CUDA_TRY(cudaGetLastError());
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)((Ns + 127) / 128), 1, 1);
+            cfg.blockDim = dim3(128, 1, 1);
+            cfg.stream = st;
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr.val.programmaticStreamSerializationAllowed = ex->pdl ? 1 : 0;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stretch_accept, walkers_dev, lnp_dev, (int)K, D, half,
+                                        (const double*)q_dev, (const double*)z_dev, (const double*)nullptr, seed,
+                                        iteration, reinterpret_cast<long long*>(naccepted_dev), pi));
         }
         if (chain_dev || lnp_chain_dev) {
             int rc = spamm_chain_record(walkers_dev, lnp_dev, K, D, (int64_t)iteration, chain_len, chain_dev,

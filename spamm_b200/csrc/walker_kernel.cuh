@@ -1095,6 +1095,10 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (warp == 0) g_trace[(size_t)blockIdx.x * 8 + 5] = t;
     }
 #endif
+    // Sharded call: its consumer (k_gather / k_stretch_accept, launched with programmatic stream serialisation)
+    // waits on the ranks' flags, not on this grid, so it may be made resident as soon as every CTA is past its
+    // tasks -- the launch latency of the consumer then overlaps this kernel's tail instead of following it.
+    if (MODE == 0 && po.bufs != nullptr) cudaTriggerProgrammaticLaunchCompletion();
     // ---- per-walker reduction in fixed chunk order + likelihood (Model.py:440-445) ----------------
     if (MODE == 0 && PARTS) {
         __syncthreads();
