@@ -27,26 +27,44 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
     return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// One stretch proposal (emcee 2.2.1 _propose_stretch) for walker i of the active half: z = ((a-1) u + 1)^2 / a and
+// the index of the complementary walker, from the Philox counter (seed, i, half, iteration).
+__device__ __forceinline__ void stretch_draw(uint64_t seed, int i, int half, uint64_t iter, double a, int K,
+                                             double& zz, int& partner) {
+    uint32_t r[4];
+    philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)half,
+               (uint32_t)iter, (uint32_t)(iter >> 32) ^ 0x50524f50u, r);
+    const double u = u53(r[0], r[1]);
+    zz = ((a - 1.0) * u + 1.0);
+    zz = zz * zz / a;
+    const int Ns = K / 2, Nc = K - Ns;
+    int rint_ = (int)(u53(r[2], r[3]) * Nc);
+    if (rint_ >= Nc) rint_ = Nc - 1;
+    partner = half == 0 ? Ns + rint_ : rint_;
+}
+
 __global__ void k_stretch_propose(const double* __restrict__ walkers, int K, int D, int half,
                                   double a, uint64_t seed, uint64_t iter, double* __restrict__ q,
                                   double* __restrict__ z) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int Ns = K / 2;
     if (i >= Ns) return;
-    uint32_t r[4];
-    philox4x32((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)half,
-               (uint32_t)iter, (uint32_t)(iter >> 32) ^ 0x50524f50u, r);
-    double u = u53(r[0], r[1]);
-    double zz = ((a - 1.0) * u + 1.0);
-    zz = zz * zz / a;
-    int Nc = K - Ns;
-    int rint_ = (int)(u53(r[2], r[3]) * Nc);
-    if (rint_ >= Nc) rint_ = Nc - 1;
+    double zz;
+    int partner;
+    stretch_draw(seed, i, half, iter, a, K, zz, partner);
     const double* s = walkers + (size_t)(half == 0 ? i : Ns + i) * D;
-    const double* cc = walkers + (size_t)(half == 0 ? Ns + rint_ : rint_) * D;
+    const double* cc = walkers + (size_t)partner * D;
     for (int d = 0; d < D; ++d) q[(size_t)i * D + d] = cc[d] - zz * (cc[d] - s[d]);
     z[i] = zz;
 }
+
+struct StretchFused {
+    int on;                    // 0: q / z come from k_stretch_propose and the chain is recorded by k_chain_record
+    double a;
+    double* chain;             // [K][chain_len][D] or null
+    double* lnp_chain;         // [K][chain_len] or null
+    long long chain_len, chain_iter;
+};
 
 // pi.bufs != nullptr (multi-GPU): lnp_q is unused; every rank's walker kernel has left its slice of the
 // proposals' ln-posteriors in its own exchange region.  Each block waits until all ranks have raised their
@@ -54,7 +72,8 @@ __global__ void k_stretch_propose(const double* __restrict__ walkers, int K, int
 __global__ void k_stretch_accept(double* __restrict__ walkers, double* __restrict__ lnp, int K,
                                  int D, int half, const double* __restrict__ q,
                                  const double* __restrict__ z, const double* lnp_q,
-                                 uint64_t seed, uint64_t iter, long long* __restrict__ nacc, PeerIn pi) {
+                                 uint64_t seed, uint64_t iter, long long* __restrict__ nacc, PeerIn pi,
+                                 StretchFused fu) {
     if (pi.bufs != nullptr) wait_flags(pi);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int Ns = K / 2;
@@ -65,11 +84,31 @@ __global__ void k_stretch_accept(double* __restrict__ walkers, double* __restric
     double u = u53(r[0], r[1]);
     int wi = half == 0 ? i : Ns + i;
     const double lq = pi.bufs != nullptr ? gathered_value(pi, i) : lnp_q[i];
-    double lnpdiff = ((double)D - 1.0) * log(z[i]) + lq - lnp[wi];
+    // fu.on: the library's own loop -- the proposal was made inside the walker kernel (k_walkers, Proposal) and is
+    // re-made here from the same counter instead of being read from q / z (the complementary half does not move
+    // during this half-step and this thread is the only writer of its own walker)
+    double zz = 0.0;
+    int partner = 0;
+    if (fu.on) stretch_draw(seed, i, half, iter, fu.a, K, zz, partner);
+    else zz = z[i];
+    double lnpdiff = ((double)D - 1.0) * log(zz) + lq - lnp[wi];
     if (lnpdiff > log(u)) {
-        for (int d = 0; d < D; ++d) walkers[(size_t)wi * D + d] = q[(size_t)i * D + d];
+        if (fu.on) {
+            const double* cc = walkers + (size_t)partner * D;
+            double* sw = walkers + (size_t)wi * D;
+            for (int d = 0; d < D; ++d) sw[d] = cc[d] - zz * (cc[d] - sw[d]);
+        } else {
+            for (int d = 0; d < D; ++d) walkers[(size_t)wi * D + d] = q[(size_t)i * D + d];
+        }
         lnp[wi] = lq;
         if (nacc) nacc[wi] += 1;
+    }
+    // ... and this half's walkers are final for the iteration: record them (k_chain_record fused)
+    if (fu.on) {
+        if (fu.chain)
+            for (int d = 0; d < D; ++d)
+                fu.chain[((size_t)wi * fu.chain_len + fu.chain_iter) * D + d] = walkers[(size_t)wi * D + d];
+        if (fu.lnp_chain) fu.lnp_chain[(size_t)wi * fu.chain_len + fu.chain_iter] = lnp[wi];
     }
 }
 

@@ -801,7 +801,7 @@ static bool canonical_order(const PlanDev& pd, uint32_t mask) {
 template <int MODE, bool CANON, bool SPLIT, int SPEC = 0>
 static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
                       const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
-                      PeerOut po) {
+                      PeerOut po, Proposal pr) {
     // (SPEC & kSpecParts: csize = 2 independent CTAs per walker, red parts first; no cluster)
     PartsWs pw{pl->d_part_chi, pl->d_part_cnt, n_walkers};
     cudaLaunchConfig_t cfg = {};
@@ -815,7 +815,7 @@ static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, 
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     if (SPLIT) { cfg.attrs = &attr; cfg.numAttrs = 1; }
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, SPEC>, pd, params_dev, w0, out_dev, mask, dr, po, pw));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, k_walkers<MODE, CANON, SPLIT, SPEC>, pd, params_dev, w0, out_dev, mask, dr, po, pw, pr));
     return SPAMM_OK;
 }
 
@@ -876,12 +876,12 @@ extern "C" int spamm_plan_specialised(const SpammPlan* pl) {
 template <int MODE>
 static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, const PlanDev& pd,
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
-                    PeerOut po) {
+                    PeerOut po, Proposal pr) {
     const int c = cluster_size_for(pl, n_walkers);
     if (MODE == 0 && c == 1 && parts_for(pl, pd, n_walkers)) {
 #define SPAMM_LAUNCH_PARTS(S)                                                                                    \
     case S:                                                                                                      \
-        return launch_one<0, true, false, S | kSpecParts>(pl, n_walkers, 2, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        return launch_one<0, true, false, S | kSpecParts>(pl, n_walkers, 2, st, pd, params_dev, w0, out_dev, mask, dr, po, pr);
         switch (spec_of(pl, pd, mask, dr)) {
             SPAMM_PARTS_LIST(SPAMM_LAUNCH_PARTS)
             default: break;
@@ -891,8 +891,8 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
     if (MODE == 0) {
 #define SPAMM_LAUNCH_SPEC(S)                                                                                     \
     case S:                                                                                                      \
-        return c > 1 ? launch_one<0, true, true, S>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po) \
-                     : launch_one<0, true, false, S>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        return c > 1 ? launch_one<0, true, true, S>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po, pr) \
+                     : launch_one<0, true, false, S>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po, pr);
         switch (spec_of(pl, pd, mask, dr)) {
             SPAMM_SPEC_LIST(SPAMM_LAUNCH_SPEC)
             default: break;
@@ -900,17 +900,18 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
 #undef SPAMM_LAUNCH_SPEC
     }
     if (c > 1) {
-        return canon ? launch_one<MODE, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po)
-                     : launch_one<MODE, false, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po);
+        return canon ? launch_one<MODE, true, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po, pr)
+                     : launch_one<MODE, false, true>(pl, n_walkers, c, st, pd, params_dev, w0, out_dev, mask, dr, po, pr);
     }
-    return canon ? launch_one<MODE, true, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po)
-                 : launch_one<MODE, false, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po);
+    return canon ? launch_one<MODE, true, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po, pr)
+                 : launch_one<MODE, false, false>(pl, n_walkers, 1, st, pd, params_dev, w0, out_dev, mask, dr, po, pr);
 }
 
 template <int MODE>
 static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev, int n_walkers,
                           double* out_dev, cudaStream_t st, bool force_direct,
-                          PeerOut po = PeerOut{nullptr, 0, 0, nullptr, 0u, 0, 0ull}) {
+                          PeerOut po = PeerOut{nullptr, 0, 0, nullptr, 0u, 0, 0ull},
+                          Proposal pr = Proposal{nullptr, 0, 0, 0, 0.0, 0ull, 0ull}) {
     const PlanDev& pd = pl->dev;
     bool need_fe = false, need_host = false;
     for (int q = 0; q < pd.n_comp; ++q) {
@@ -921,7 +922,7 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
     bool direct = (need_fe || need_host) && (force_direct || pl->template_mode == SPAMM_TEMPLATES_DIRECT);
     if (!direct) {
         DirectRows dr{nullptr, nullptr, nullptr, nullptr};
-        int rc = launch_k<MODE>(pl, canonical_order(pd, mask), n_walkers, st, pd, params_dev, 0, out_dev, mask, dr, po);
+        int rc = launch_k<MODE>(pl, canonical_order(pd, mask), n_walkers, st, pd, params_dev, 0, out_dev, mask, dr, po, pr);
         if (rc) return rc;
         pl->launches += 1;
         return SPAMM_OK;
@@ -942,7 +943,7 @@ static int launch_walkers(SpammPlan* pl, uint32_t mask, const double* params_dev
             dr.host_f = pl->d_host_f; dr.host_nf = pl->d_host_nf;
         }
         double* o = MODE == 0 ? out_dev : out_dev + (size_t)w0 * pd.P;
-        if ((rc = launch_k<MODE>(pl, canonical_order(pd, mask), nW, st, pd, params_dev, w0, o, mask, dr, po))) return rc;
+        if ((rc = launch_k<MODE>(pl, canonical_order(pd, mask), nW, st, pd, params_dev, w0, o, mask, dr, po, pr))) return rc;
         pl->launches += 1;
     }
     return SPAMM_OK;
@@ -1071,7 +1072,8 @@ extern "C" int spamm_stretch_accept(double* walkers_dev, double* lnp_dev, int32_
     int Ns = K / 2;
     k_stretch_accept<<<(Ns + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
         walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed, iteration,
-        reinterpret_cast<long long*>(naccepted_dev), PeerIn{nullptr, 0, 0, 0, 1, 0ull, nullptr, nullptr});
+        reinterpret_cast<long long*>(naccepted_dev), PeerIn{nullptr, 0, 0, 0, 1, 0ull, nullptr, nullptr},
+        StretchFused{0, 0.0, nullptr, nullptr, 0, 0});
     CUDA_TRY(cudaGetLastError());
     return SPAMM_OK;
 }
@@ -1098,19 +1100,36 @@ extern "C" int spamm_stretch_run(SpammPlan* pl, double* walkers_dev, double* lnp
     if (!pl->has_data) return set_error(SPAMM_EINVAL, "plan was created without data flux/flux_error");
     if ((chain_dev || lnp_chain_dev) && (int64_t)iter0 + n_iter > chain_len)
         return set_error(SPAMM_EINVAL, "chain buffer too short");
-    const int D = pl->dev.D;
+    const int D = pl->dev.D, Ns = K / 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    // Pre-broadened bank: two launches per half-step -- the walker kernel makes the proposal itself (Proposal) and
+    // the accept kernel re-makes it from the same counter and records the chain (StretchFused).  Per-walker
+    // broadening needs the proposals in memory for its row kernels and keeps the propose / record launches.
+    const bool fused = pl->template_mode != SPAMM_TEMPLATES_DIRECT;
     for (int it = 0; it < n_iter; ++it) {
         const uint64_t iteration = iter0 + (uint64_t)it;
         for (int half = 0; half < 2; ++half) {
-            int rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream);
-            if (rc) return rc;
-            if ((rc = launch_walkers<0>(pl, full_mask(pl), q_dev, K / 2, lnp_q_dev, (cudaStream_t)stream, false)))
+            int rc;
+            if (!fused) {
+                if ((rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream)))
+                    return rc;
+                if ((rc = launch_walkers<0>(pl, full_mask(pl), q_dev, Ns, lnp_q_dev, st, false))) return rc;
+                if ((rc = spamm_stretch_accept(walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed,
+                                               iteration, naccepted_dev, stream)))
+                    return rc;
+                continue;
+            }
+            Proposal pr{walkers_dev, K, half, 0, a, seed, iteration};
+            if ((rc = launch_walkers<0>(pl, full_mask(pl), walkers_dev, Ns, lnp_q_dev, st, false,
+                                        PeerOut{nullptr, 0, 0, nullptr, 0u, 0, 0ull}, pr)))
                 return rc;
-            if ((rc = spamm_stretch_accept(walkers_dev, lnp_dev, K, D, half, q_dev, z_dev, lnp_q_dev, seed,
-                                           iteration, naccepted_dev, stream)))
-                return rc;
+            k_stretch_accept<<<(Ns + 127) / 128, 128, 0, st>>>(
+                walkers_dev, lnp_dev, K, D, half, nullptr, nullptr, lnp_q_dev, seed, iteration,
+                reinterpret_cast<long long*>(naccepted_dev), PeerIn{nullptr, 0, 0, 0, 1, 0ull, nullptr, nullptr},
+                StretchFused{1, a, chain_dev, lnp_chain_dev, (long long)chain_len, (long long)iteration});
+            CUDA_TRY(cudaGetLastError());
         }
-        if (chain_dev || lnp_chain_dev) {
+        if (!fused && (chain_dev || lnp_chain_dev)) {
             int rc = spamm_chain_record(walkers_dev, lnp_dev, K, D, (int64_t)iteration, chain_len, chain_dev,
                                         lnp_chain_dev, stream);
             if (rc) return rc;
@@ -1250,7 +1269,7 @@ extern "C" uint64_t spamm_exchange_epoch(const SpammExchange* ex) { return ex ? 
 // queue one sharded evaluation of params_dev[n_total][D]: this rank's slice through k_walkers, results into this
 // rank's region, flag raised in every region; *pi_out tells a consumer where the gathered vector lives
 static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_dev, int32_t n_total,
-                        cudaStream_t st, PeerIn* pi_out) {
+                        cudaStream_t st, PeerIn* pi_out, Proposal pr = Proposal{nullptr, 0, 0, 0, 0.0, 0ull, 0ull}) {
     if (!ex->connected) return set_error(SPAMM_EINVAL, "exchange is not connected");
     if (n_total > ex->max_n) return set_error(SPAMM_EINVAL, "exchange region holds fewer walkers than n_total");
     const uint64_t e = ++ex->epoch;
@@ -1259,8 +1278,9 @@ static int sharded_eval(SpammPlan* pl, SpammExchange* ex, const double* params_d
     const long long boff = kFlagWords + (long long)(e & 1) * ex->max_n;
     PeerOut po{ex->d_peer_ptrs, ex->n_ranks, boff + lo, ex->d_done, (unsigned)(hi - lo), ex->rank, e};
     if (hi > lo) {
+        pr.i0 = (int)lo;                 // (proposal mode: walker w of the launch is proposal lo + w of the half)
         int rc = launch_walkers<0>(pl, full_mask(pl), params_dev + (size_t)lo * pl->dev.D, (int)(hi - lo), nullptr, st,
-                                   false, po);
+                                   false, po, pr);
         if (rc) return rc;
     } else {
         k_raise_flags<<<1, 1, 0, st>>>(po);
@@ -1362,13 +1382,16 @@ extern "C" int spamm_stretch_run_sharded(SpammPlan* pl, SpammExchange* ex, doubl
         return set_error(SPAMM_EINVAL, "chain buffer too short");
     const int D = pl->dev.D, Ns = K / 2;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool fused = pl->template_mode != SPAMM_TEMPLATES_DIRECT;      // see spamm_stretch_run
     for (int it = 0; it < n_iter; ++it) {
         const uint64_t iteration = iter0 + (uint64_t)it;
         for (int half = 0; half < 2; ++half) {
-            int rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream);
-            if (rc) return rc;
+            int rc;
+            if (!fused && (rc = spamm_stretch_propose(walkers_dev, K, D, half, a, seed, iteration, q_dev, z_dev, stream)))
+                return rc;
             PeerIn pi;
-            if ((rc = sharded_eval(pl, ex, q_dev, Ns, st, &pi))) return rc;
+            Proposal pr{fused ? walkers_dev : nullptr, K, half, 0, a, seed, iteration};
+            if ((rc = sharded_eval(pl, ex, fused ? walkers_dev : q_dev, Ns, st, &pi, pr))) return rc;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)((Ns + 127) / 128), 1, 1);
             cfg.blockDim = dim3(128, 1, 1);
@@ -1378,11 +1401,12 @@ extern "C" int spamm_stretch_run_sharded(SpammPlan* pl, SpammExchange* ex, doubl
             attr.val.programmaticStreamSerializationAllowed = ex->pdl ? 1 : 0;
             cfg.attrs = &attr;
             cfg.numAttrs = 1;
+            StretchFused fu{fused ? 1 : 0, a, chain_dev, lnp_chain_dev, (long long)chain_len, (long long)iteration};
             CUDA_TRY(cudaLaunchKernelEx(&cfg, k_stretch_accept, walkers_dev, lnp_dev, (int)K, D, half,
                                         (const double*)q_dev, (const double*)z_dev, (const double*)nullptr, seed,
-                                        iteration, reinterpret_cast<long long*>(naccepted_dev), pi));
+                                        iteration, reinterpret_cast<long long*>(naccepted_dev), pi, fu));
         }
-        if (chain_dev || lnp_chain_dev) {
+        if (!fused && (chain_dev || lnp_chain_dev)) {
             int rc = spamm_chain_record(walkers_dev, lnp_dev, K, D, (int64_t)iteration, chain_len, chain_dev,
                                         lnp_chain_dev, stream);
             if (rc) return rc;

@@ -133,6 +133,18 @@ __global__ void __launch_bounds__(256) k_gather(PeerIn pi, int n_total, double* 
     if (copy != nullptr) copy[i] = v;
 }
 
+// The library's sampler loop lets the walker kernel make the stretch proposal itself (no propose kernel, no q / z
+// round trip through memory): walker w of the launch is proposal i0 + w of the active half, and its parameter
+// vector is c_j - z (c_j - s_i) drawn from the Philox counter exactly as k_stretch_propose / stretch_draw do.
+struct Proposal {
+    const double* walkers;     // [K][D] ensemble; null: parameters come from `params`
+    int K, half, i0;
+    double a;
+    unsigned long long seed, iter;
+};
+__device__ __forceinline__ void stretch_draw(uint64_t seed, int i, int half, uint64_t iter, double a, int K,
+                                             double& zz, int& partner);
+
 // Walker PARTS (kSpecParts instantiations): a walker is evaluated by two independent CTAs -- the "red" part
 // takes the 64-pixel chunks from PlanDev::part_chunk (just blueward of the Balmer edge) on and builds the line
 // table and cluster moments, the "blue" part takes the chunks before it and stages the Balmer continuum -- so
@@ -491,7 +503,7 @@ static_assert((9 | kSpecNoBpc) == 41 && (9 | kSpecNoBc) == 73 && (15 | kSpecNoBp
 template <int MODE, bool CANON, bool SPLIT, int SPECP>
 __global__ void __launch_bounds__(kThreads, SPAMM_MIN_BLOCKS)
 k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* __restrict__ out,
-          uint32_t mask, DirectRows dr, PeerOut po, PartsWs pw) {
+          uint32_t mask, DirectRows dr, PeerOut po, PartsWs pw, Proposal pr) {
     constexpr int SPEC = SPECP & ~kSpecParts;
     constexpr bool PARTS = (SPECP & kSpecParts) != 0;
     static_assert(!PARTS || (!SPLIT && MODE == 0 && (SPEC & kSpecBalmer) && !(SPEC & (kSpecNoBpc | kSpecNoBc))),
@@ -546,7 +558,18 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     if (tid == 0) { c.prior_ok = 1; c.task_next = 0; }
     __syncthreads();
     if (tid < pl.D) {
-        double v = pwalk[tid];
+        double v;
+        if (pr.walkers != nullptr) {
+            const int i = pr.i0 + w, Ns = pr.K / 2;
+            double zz;
+            int partner;
+            stretch_draw(pr.seed, i, pr.half, pr.iter, pr.a, pr.K, zz, partner);
+            const double sd = pr.walkers[(size_t)(pr.half == 0 ? i : Ns + i) * pl.D + tid];
+            const double cd = pr.walkers[(size_t)partner * pl.D + tid];
+            v = cd - zz * (cd - sd);
+        } else {
+            v = pwalk[tid];
+        }
         c.p[tid] = v;
 
         if (MODE == 0 && pl.lo != nullptr) {
