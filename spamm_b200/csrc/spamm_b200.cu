@@ -79,7 +79,8 @@ struct SpammPlan {
     int* h_status = nullptr;           // pinned copy of the device status word (mapped; see deferred_status)
     double* d_part_chi = nullptr;      // walker parts: per-chunk chi^2 partials [max_walkers][n_chunks]
     unsigned* d_part_cnt = nullptr;    //               arrival counters [max_walkers]
-    int parts_max_walkers = getenv("SPAMM_PARTS_MAX") ? atoi(getenv("SPAMM_PARTS_MAX")) : 0;   // auto two-part split up to here (0: default)
+    int parts_max_walkers = getenv("SPAMM_PARTS_MAX") ? atoi(getenv("SPAMM_PARTS_MAX")) : 0;   // auto: mixed launches up to this many waves (0: default)
+    int parts_mixed = getenv("SPAMM_PARTS_MIXED") ? atoi(getenv("SPAMM_PARTS_MIXED")) : 1;     // 0: never mix; 2: mix from one wave on
     bool use_full_kernel = getenv("SPAMM_NO_FULL_KERNEL") == nullptr;   // tests compare it with the generic one
 };
 
@@ -796,16 +797,21 @@ static bool canonical_order(const PlanDev& pd, uint32_t mask) {
     return true;
 }
 
+static int parts_count(const SpammPlan* pl, int n_walkers);
+
 // One launch of the fused kernel.  Ensembles too small to fill the GPU (fewer walkers than
 // resident CTA slots) run one walker per thread-block cluster of 2/4/8 CTAs (SPLIT instantiation).
 template <int MODE, bool CANON, bool SPLIT, int SPEC = 0>
 static int launch_one(SpammPlan* pl, int n_walkers, int csize, cudaStream_t st, const PlanDev& pd,
                       const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                       PeerOut po, Proposal pr) {
-    // (SPEC & kSpecParts: csize = 2 independent CTAs per walker, red parts first; no cluster)
-    PartsWs pw{pl->d_part_chi, pl->d_part_cnt, n_walkers};
+    // (SPEC & kSpecParts: the launch's last n_parts walkers run as two independent CTAs each -- red parts first --
+    //  after the n_whole walkers that run one CTA each; no cluster)
+    int n_parts = 0;
+    if (SPEC & kSpecParts) n_parts = parts_count(pl, n_walkers);
+    PartsWs pw{pl->d_part_chi, pl->d_part_cnt, n_walkers - n_parts, n_parts};
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_walkers * csize), 1, 1);
+    cfg.gridDim = dim3((unsigned)((SPEC & kSpecParts) ? n_walkers + n_parts : n_walkers * csize), 1, 1);
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = pl->smem_bytes;
     cfg.stream = st;
@@ -828,17 +834,28 @@ static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
     return c;
 }
 
-// Two independent CTAs per walker (kSpecParts)?  Forced by split mode 3; automatic for ensembles of a few
-// waves of CTAs, where halving the work items shortens the tail of the last wave.
-static bool parts_for(const SpammPlan* pl, const PlanDev& pd, int n_walkers) {
-    if (pd.part_chunk < 0 || !pl->d_part_chi || n_walkers > pl->max_walkers) return false;
-    if (pl->split_mode == 3) return true;
-    if (pl->split_mode != 1) return false;
-    // measured on B200 (profiles/r02_split_table.txt): ahead of one CTA per walker from about half a wave of
-    // CTAs (the two parts of a walker can land on different SMs) up to about a wave and a half
+// How many walkers of an n-walker launch run as two independent CTAs (kSpecParts; the rest one CTA each).
+// Forced by split mode 3 (all of them).  Automatic (profiles/r02_split_table.txt): below a wave and a half of
+// CTAs every walker -- the two parts of a walker can land on different SMs, which evens out the 3-versus-4
+// walkers per SM of a partial wave -- and for a few waves the walkers of the last, partial wave only, so its tail
+// is made of finer work items; long launches (where CTAs of all phases overlap anyway) and ensembles small
+// enough for the cluster split are left alone.
+static int parts_count(const SpammPlan* pl, int n_walkers) {
+    const PlanDev& pd = pl->dev;
+    if (pd.part_chunk < 0 || !pl->d_part_chi || n_walkers > pl->max_walkers) return 0;
+    if (pl->split_mode == 3) return n_walkers;
+    if (pl->split_mode != 1) return 0;
     const int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
-    const int hi = pl->parts_max_walkers > 0 ? pl->parts_max_walkers : 3 * slots / 2;
-    return 2 * n_walkers > slots && n_walkers <= hi;
+    if (3 * n_walkers <= slots) return 0;                                 // cluster split territory
+    if (2 * n_walkers <= 3 * slots && pl->parts_mixed < 2) return n_walkers;
+    const int max_waves = pl->parts_max_walkers > 0 ? pl->parts_max_walkers : 4;
+    if (!pl->parts_mixed || n_walkers > max_waves * slots) return 0;
+    return n_walkers % slots;                                             // the partial wave
+}
+
+static bool parts_for(const SpammPlan* pl, const PlanDev& pd, int n_walkers) {
+    (void)pd;
+    return parts_count(pl, n_walkers) > 0;
 }
 
 // Which specialised instantiation (SPEC bit set, 0 = none) serves ln-posterior calls on this plan

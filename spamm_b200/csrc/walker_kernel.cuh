@@ -150,10 +150,13 @@ __device__ __forceinline__ void stretch_draw(uint64_t seed, int i, int half, uin
 // table and cluster moments, the "blue" part takes the chunks before it and stages the Balmer continuum -- so
 // neither repeats the other's share of the prologue.  Each part leaves its per-chunk chi^2 partials in `chi`;
 // the part that finishes second sums all of them in the unsplit kernel's fixed order (bit-identical result).
+// A launch may mix the two forms: its first n_whole walkers run one CTA each (the full waves of CTAs), the
+// n_parts walkers after them two CTAs each (the last, partial wave, where finer work items shorten the tail).
 struct PartsWs {
-    double* chi;           // [n_walkers][n_chunks]
-    unsigned* cnt;         // [n_walkers], zero between launches
-    int n_walkers;         // blocks [0, n) are the red parts, [n, 2n) the blue parts
+    double* chi;           // [walkers][n_chunks]
+    unsigned* cnt;         // [walkers], zero between launches
+    int n_whole;           // blocks [0, n_whole): one whole walker each
+    int n_parts;           // then n_parts red parts, then n_parts blue parts (walkers n_whole ... n_whole + n_parts - 1)
 };
 
 // Storey & Hummer table look-up: kx=ky=1 FITPACK spline == clamped bilinear
@@ -528,11 +531,13 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // PARTS: is_red builds the line table / moments and owns chunks >= part_chunk, is_blue stages the whole
     // Balmer continuum and owns the chunks before it (both true: the whole walker in one CTA)
     bool is_red = true, is_blue = true;
-    if (PARTS) {
-        is_red = (int)blockIdx.x < pw.n_walkers;
+    if (PARTS && (int)blockIdx.x >= pw.n_whole) {
+        const int b = (int)blockIdx.x - pw.n_whole;
+        is_red = b < pw.n_parts;
         is_blue = !is_red;
-        if (is_blue) wloc -= pw.n_walkers;
+        wloc = pw.n_whole + (is_red ? b : b - pw.n_parts);
     }
+    const bool only_red = PARTS && !is_blue, only_blue = PARTS && !is_red;
     const int w = w0 + wloc;
     const int P = pl.P;
     const double* pwalk = params + (size_t)w * pl.D;
@@ -729,7 +734,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
         if (FULL && pl.bc_pair_ok && pl.bc_dhnu_max * inv_kT <= 0.01) {
             // adjacent pixel pairs, one pair per trip, the next pair's loads issued before this pair's arithmetic
             // (a red part needs the samples under its own Balmer-continuum pixels and the normaliser only)
-            int k = (PARTS && is_red ? pl.part_stage0 : 0) + 2 * tid;
+            int k = (only_red ? pl.part_stage0 : 0) + 2 * tid;
             double2 h, kk, t3;
             if (k < nst) {
                 h = *reinterpret_cast<const double2*>(pl.bc_hnu + k);
@@ -750,7 +755,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             }
         } else {
             // one pixel per trip, the next pixel's loads issued before this pixel's arithmetic
-            int k = (PARTS && is_red ? pl.part_stage0 : 0) + tid;
+            int k = (only_red ? pl.part_stage0 : 0) + tid;
             double h = 0.0, kk = 0.0, t3 = 0.0;
             if (k < nst) { h = pl.bc_hnu[k]; kk = pl.bc_K[k]; t3 = pl.bc_t3[k]; }
 #pragma unroll 1
@@ -886,8 +891,8 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // a plain atom.shared into its warp-aggregation sequence -- and measured 2.7 % slower, 1 % slower
     // when tasks are fetched in pairs, although the one task inside the line forest, ~13x the work of
     // the others, leaves its warp behind: the SM's other CTAs fill the gap.)
-    const int chunk_top = PARTS && is_blue ? pl.part_chunk : n_chunks;        // this CTA owns chunks
-    const int chunk_bot = PARTS && is_red ? pl.part_chunk : 0;                //   [chunk_bot, chunk_top)
+    const int chunk_top = only_blue ? pl.part_chunk : n_chunks;               // this CTA owns chunks
+    const int chunk_bot = only_red ? pl.part_chunk : 0;                       //   [chunk_bot, chunk_top)
     // PARTS (ensembles of a few waves, where nothing fills the gap a straggling warp leaves): tasks are dealt
     // dynamically, and a red part starts with its chunks next to the Balmer edge -- inside the line forest, an
     // order of magnitude more work than a far chunk -- so the CTA's tail is made of light tasks
@@ -897,7 +902,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
             t = __shfl_sync(0xffffffffu, t, 0);
         }
         if (t >= chunk_top - chunk_bot) break;
-        const int chunk = PARTS && is_red ? chunk_bot + t : chunk_top - 1 - t;
+        const int chunk = only_red ? chunk_bot + t : chunk_top - 1 - t;
         // pixels i0 + 32 q; per-pixel arrays carry kChunk elements of slack, so no clamping
         // PAIR (FULL kernel): lane l holds the adjacent pixels 2l, 2l+1 of the chunk, fetched with 16-byte
         // loads; otherwise pixels l and l + 32
@@ -1123,7 +1128,7 @@ k_walkers(const PlanDev pl, const double* __restrict__ params, int w0, double* _
     // tasks -- the launch latency of the consumer then overlaps this kernel's tail instead of following it.
     if (MODE == 0 && po.bufs != nullptr) cudaTriggerProgrammaticLaunchCompletion();
     // ---- per-walker reduction in fixed chunk order + likelihood (Model.py:440-445) ----------------
-    if (MODE == 0 && PARTS) {
+    if (MODE == 0 && PARTS && (only_red || only_blue)) {
         __syncthreads();
         double* gchi = pw.chi + (size_t)wloc * n_chunks;
         for (int k = chunk_bot + tid; k < chunk_top; k += kThreads) gchi[k] = sChi[k];
