@@ -677,7 +677,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--walkers", type=int, default=N_WALKERS, help="walkers of the (one) ensemble")
     ap.add_argument("--sustained", type=float, default=5.0, help="seconds of the sustained leg (0: skip; N = 1 only)")
-    ap.add_argument("--sampler-iterations", type=int, default=40)
+    ap.add_argument("--sampler-iterations", type=int, default=100,
+                    help="iterations of the timed device-sampler run (its fixed costs -- state upload, broadcast, the "
+                         "first evaluation, result download -- are inside the wall clock)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-line-sum comparison run")
     ap.add_argument("--no-sampler", action="store_true", help="skip the device-sampler figure")
