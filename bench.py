@@ -569,7 +569,7 @@ def run_ours(args):
             "frac": achieved / float(peak.value) if achieved and peak.value else None,
             "traffic": prof.get("dram_bytes_per_launch"),
             "kernel": "k_walkers<0, true, false, 15%s> (full-model instantiation), %d walkers per launch"
-                      % (" | parts" if world > 1 and plan_uses_parts(per_gpu) else "", per_gpu),
+                      % (" | 128: walkers of the partial wave as two CTAs" if plan_uses_parts(per_gpu) else "", per_gpu),
             "launch_ms": launch_ms,
             "what": "frac = FP64 flops the kernel EXECUTES per evaluation (ncu: 2 x DFMA + DADD + DMUL thread "
                     "instructions, profiles/k_walkers_traffic.json) x evaluations/s of the launch / measured DFMA peak",
@@ -663,10 +663,12 @@ def run_ours(args):
 
 
 def plan_uses_parts(n):
-    """Mirror of the library's automatic choice (spamm_b200.cu parts_for): two CTAs per walker between half a
-    wave and a wave and a half of CTAs."""
+    """Mirror of the library's automatic choice (spamm_b200.cu parts_count): from a third of a wave of CTAs up to
+    four waves some or all walkers of a launch run as two independent CTAs (the kSpecParts instantiation)."""
     slots = 148 * 4
-    return 2 * n > slots and n <= 3 * slots // 2
+    if 3 * n <= slots or n > 4 * slots:
+        return False
+    return 2 * n <= 3 * slots or n % slots != 0
 
 
 def main():
