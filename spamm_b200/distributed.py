@@ -50,6 +50,23 @@ def shard_bounds(n, world, rank):
     return lo, hi, per
 
 
+def replicate_object(obj, group=None):
+    """Rank 0's picklable object on every rank (the sampler's seed: each rank's own numpy RNG would draw a
+    different one and the ranks would silently propose different moves)."""
+    if world_info()[1] == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def replicate_tensor(t, group=None):
+    """Overwrite `t` on every rank with rank 0's values (the sampler's start state); returns t."""
+    if world_info()[1] > 1:
+        dist.broadcast(t, src=0, group=group)
+    return t
+
+
 class ShardedLnPost(object):
     """ln-posterior of [n, D] parameters evaluated as one slice per rank.
 

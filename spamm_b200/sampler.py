@@ -87,17 +87,14 @@ class EnsembleSampler(object):
         # exchange (walker kernel stores into every rank's region over NVLink + flags; the whole loop runs
         # inside spamm_stretch_run_sharded).  SPAMM_EXCHANGE=nccl: all-gather per half-step from Python.
         import os
-        from .distributed import ShardedLnPost, ExchangeLnPost, Exchange, world_info
+        from .distributed import ShardedLnPost, ExchangeLnPost, Exchange, world_info, replicate_object
         self.exchange = "single"
         self._xch = None
         self.rank, self.world = world_info()
         if self.world > 1:
-            import torch.distributed as dist
             # every rank proposes the whole half-ensemble from the same counter-based RNG: the seed (and, in
             # run_mcmc, the start state) must be rank 0's, whatever each rank's own numpy RNG drew
-            box = [self.seed]
-            dist.broadcast_object_list(box, src=0)
-            self.seed = int(box[0])
+            self.seed = int(replicate_object(self.seed))
             if os.environ.get("SPAMM_EXCHANGE", "p2p") == "p2p" and ExchangeLnPost.available():
                 self._xch = Exchange(nwalkers)
                 self._evaluate = ExchangeLnPost(self.plan, nwalkers, exchange=self._xch)
@@ -199,9 +196,8 @@ class EnsembleSampler(object):
             raise ValueError("At least one parameter value was NaN.")
         dev = torch.device("cuda", torch.cuda.current_device())
         self._walkers = torch.from_numpy(p0).to(dev)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.broadcast(self._walkers, src=0)         # the replicated state is rank 0's
+        from .distributed import replicate_tensor
+        replicate_tensor(self._walkers)                  # the replicated state is rank 0's
         self._q = torch.empty((self.k // 2, self.dim), dtype=torch.float64, device=dev)
         self._z = torch.empty(self.k // 2, dtype=torch.float64, device=dev)
         if self._nacc is None:
@@ -210,8 +206,7 @@ class EnsembleSampler(object):
             self._lnp = self._evaluate(self._walkers).clone()
         else:
             self._lnp = torch.from_numpy(np.array(lnprob0, dtype=np.float64)).to(dev)
-            if self.world > 1:
-                dist.broadcast(self._lnp, src=0)
+            replicate_tensor(self._lnp)
         if bool(torch.isnan(self._lnp).any()):
             raise ValueError("The initial lnprob was NaN.")
         start = self.iterations

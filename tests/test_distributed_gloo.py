@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from spamm_b200.distributed import ShardedLnPost, shard_bounds
+from spamm_b200.distributed import ShardedLnPost, shard_bounds, replicate_object, replicate_tensor
 
 
 def _free_port():
@@ -43,6 +43,11 @@ def _worker(rank, world, port, n, out_dir):
     np.save(os.path.join(out_dir, "r%d.npy" % rank), res.numpy())
     np.save(os.path.join(out_dir, "s%d.npy" % rank), res2.numpy())
     np.save(os.path.join(out_dir, "c%d.npy" % rank), np.array(calls))
+    # the sampler's replicated state: every rank draws its own seed and start positions, rank 0's must win
+    seed = replicate_object(1000 + rank)
+    start = replicate_tensor(torch.full((4, 3), float(rank + 1), dtype=torch.float64))
+    np.save(os.path.join(out_dir, "seed%d.npy" % rank), np.array([seed]))
+    np.save(os.path.join(out_dir, "start%d.npy" % rank), start.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,6 +68,8 @@ def test_sharded_lnpost_world2(tmp_path, n):
         calls = np.load(tmp_path / ("c%d.npy" % r))
         lo, hi, _ = shard_bounds(n, world, r)
         assert calls[0] == hi - lo                     # each rank evaluated only its slice
+        assert np.load(tmp_path / ("seed%d.npy" % r))[0] == 1000
+        assert np.array_equal(np.load(tmp_path / ("start%d.npy" % r)), np.full((4, 3), 1.0))
 
 
 def test_shard_bounds_cover_everything():
