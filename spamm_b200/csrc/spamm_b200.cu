@@ -829,7 +829,8 @@ static int cluster_size_for(const SpammPlan* pl, int n_walkers) {
     if (pl->split_mode == 0 || pl->split_mode == 3) return 1;
     int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
     int c = 1;
-    while (c < 8 && n_walkers * c * 4 <= slots) c *= 2;       // keep the split grid within half the slots
+    while (c < 8 && n_walkers * c * 5 <= slots * 2) c *= 2;   // keep the split grid within ~0.8 of the slots
+                                                              // (profiles/r02_split_table.txt: 96 walkers x4 35 us, x2 41)
     if (pl->split_mode > 1) c = pl->split_mode;          // forced (tests)
     return c;
 }
@@ -846,7 +847,7 @@ static int parts_count(const SpammPlan* pl, int n_walkers) {
     if (pl->split_mode == 3) return n_walkers;
     if (pl->split_mode != 1) return 0;
     const int slots = pl->n_sm * SPAMM_MIN_BLOCKS;
-    if (3 * n_walkers <= slots) return 0;                                 // cluster split territory
+    if (5 * n_walkers <= slots) return 0;                                 // below ~120 walkers: cluster split
     if (2 * n_walkers <= 3 * slots && pl->parts_mixed < 2) return n_walkers;
     const int max_waves = pl->parts_max_walkers > 0 ? pl->parts_max_walkers : 4;
     if (!pl->parts_mixed || n_walkers > max_waves * slots) return 0;
@@ -894,8 +895,7 @@ template <int MODE>
 static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, const PlanDev& pd,
                     const double* params_dev, int w0, double* out_dev, uint32_t mask, DirectRows dr,
                     PeerOut po, Proposal pr) {
-    const int c = cluster_size_for(pl, n_walkers);
-    if (MODE == 0 && c == 1 && parts_for(pl, pd, n_walkers)) {
+    if (MODE == 0 && parts_for(pl, pd, n_walkers)) {
 #define SPAMM_LAUNCH_PARTS(S)                                                                                    \
     case S:                                                                                                      \
         return launch_one<0, true, false, S | kSpecParts>(pl, n_walkers, 2, st, pd, params_dev, w0, out_dev, mask, dr, po, pr);
@@ -905,6 +905,7 @@ static int launch_k(SpammPlan* pl, bool canon, int n_walkers, cudaStream_t st, c
         }
 #undef SPAMM_LAUNCH_PARTS
     }
+    const int c = cluster_size_for(pl, n_walkers);
     if (MODE == 0) {
 #define SPAMM_LAUNCH_SPEC(S)                                                                                     \
     case S:                                                                                                      \
