@@ -573,6 +573,27 @@ def test_specialised_kernel_on_awkward_grids(monkeypatch):
         assert full.status() == 0
 
 
+@pytest.mark.parametrize("W", [120, 333, 512, 700, 1024, 1536, 2100])
+def test_automatic_split_of_mid_sized_ensembles_is_bit_identical(W):
+    """Between ~120 walkers and four waves of CTAs the automatic choice runs some or all walkers of a launch as
+    two independent CTAs (red part: pixels from the Balmer edge on + line table; blue part: the pixels before it
+    + the continuum stage; per-chunk chi^2 partials through a scratch row, summed by the part that arrives
+    second in the unsplit kernel's order) -- for a few waves only the walkers of the last, partial wave (mixed
+    grid).  Same bits as one CTA per walker, out-of-prior walkers and the proposal-in-kernel form included."""
+    from spamm_b200.synth import full_model_workload
+    model, params = full_model_workload(n_pix=8192, n_walkers=W, seed=42)
+    params[::17, 1] = 1e3                          # some walkers outside the slope prior -> -inf, early exit
+    plan = model.plan
+    plan.set_walker_split(0)
+    base = plan.lnposterior_host(params)
+    assert np.isneginf(base[::17]).all() and np.isfinite(base).sum() > W // 2
+    for split in (3, 1):
+        plan.set_walker_split(split)
+        got = plan.lnposterior_host(params)
+        assert np.array_equal(got, base), (W, split)
+    assert plan.status() == 0
+
+
 @pytest.mark.parametrize("name", ["cfg2_nc_fe", "cfg3_nc_hg", "cfg4_nc_bc", "cfg5_full"])
 def test_specialised_instantiations_of_the_baseline_configs(name, monkeypatch):
     """BASELINE configs 2-5 each run their own compile-time specialised instantiation (NC+Fe, NC+host,
